@@ -1,0 +1,140 @@
+/*
+ * sb200.h — C ABI of the sliders_b200 CUDA extension (libsb200.so, sm_100a only).
+ *
+ * This is the drop-in boundary for the per-timestep UNet denoise of rohitgandikota/sliders. The reference
+ * has no FFI of its own (it is pure Python on top of diffusers/torch); the entry points below are what a
+ * Python host binds with ctypes and each one names the reference call it replaces
+ * (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative sb200_status on failure; the message of the last
+ *     failure on the calling thread is returned by sb200_last_error();
+ *   - no function allocates device memory, owns a buffer or synchronises: the caller (torch) owns every
+ *     tensor and passes raw device pointers, element counts / strides in ELEMENTS, and the cudaStream_t
+ *     (as void*) the work is enqueued on; all entry points are capturable in a CUDA graph;
+ *   - activations are bf16, channels-last: an image tensor is [B, H, W, C] == a token matrix [B*H*W, C];
+ *   - nothing throws across the boundary; shapes are validated on the host.
+ */
+#ifndef SB200_H_
+#define SB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sb200_status {
+  SB200_OK = 0,
+  SB200_ERR_INVALID = -1,   /* bad shape / alignment / flag combination */
+  SB200_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed */
+  SB200_ERR_UNSUPPORTED = -3 /* device is not sm_100 */
+} sb200_status;
+
+/* epilogue flags of sb200_gemm / sb200_conv3x3 */
+enum {
+  SB200_EPI_BIAS = 1,     /* + bias[n] */
+  SB200_EPI_ROWBIAS = 2,  /* + rowbias[(m / rows_per_batch) * N + n]   (ResnetBlock2D time-embedding add) */
+  SB200_EPI_RESID = 4,    /* + resid[m * ldr + n] */
+  SB200_EPI_GEGLU = 8,    /* out[m, j] = acc[m, j] * gelu_erf(acc[m, N/2 + j]),  j < N/2 */
+  SB200_EPI_LORA = 16     /* + scale * (X . down^T) . up^T, rank r, computed in the same tile loop */
+};
+
+/* ABI / build identification: "sb200 <version> sm_100a". */
+const char* sb200_version(void);
+const char* sb200_last_error(void);
+
+/* Per-device context: caches TMA descriptors and the SM count. */
+int sb200_create(int device, void** handle);
+int sb200_destroy(void* handle);
+
+/* LoRA side inputs of a fused GEMM / conv (reference: LoRAModule.forward, trainscripts/textsliders/lora.py:108-112).
+ *   down : [rt, K] bf16, row j = lora_down.weight row (conv: [r, kh, kw, Cin] flattened tap-major); rows
+ *          beyond the used ranks must be zero; rt is 16 or 32.
+ *   up   : [N, r] bf16 (lora_up.weight); output column n uses down rows [(n / group_n) * r, +r), so one call
+ *          can carry several adapted leaves that share an input (to_q|to_k|to_v fused: group_n = C).
+ *   scale: multiplier * alpha / rank, a run-time scalar (the slider value changes per denoise step,
+ *          eval-scripts/generate_images_xl.py:327-330). */
+typedef struct sb200_lora {
+  const void* down;
+  const void* up;
+  int r;
+  int rt;
+  int group_n;
+  float scale;
+} sb200_lora;
+
+/* out[M, N] = epilogue( X[M, K] . W[N, K]^T )  — every nn.Linear on the path and the 1x1 conv_shortcut.
+ * Replaces: torch Linear inside diffusers Attention / FeedForward / Transformer2DModel as called from
+ * trainscripts/textsliders/train_util.py:242-247, with lora.py:108-112 folded in.
+ * X may be split along K into two sources (skip-connection concat): columns [0, K0) come from x0 and
+ * [K0, K) from x1 (x1 == NULL, K0 == K for a single source). K0 and K must be multiples of 64, N of 16.
+ * bn is the N tile (0 = choose). */
+int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, const void* x1, int ldx1, int K0,
+               const void* w, int ldw, void* out, int ldo, int M, int N, int K, int flags,
+               const void* bias, const void* rowbias, int rows_per_batch, const void* resid, int ldr,
+               const sb200_lora* lora, int bn);
+
+/* 3x3 convolution, padding 1, stride 1 or 2, as an implicit GEMM over NHWC activations.
+ * Replaces: torch Conv2d inside diffusers ResnetBlock2D / Downsample2D / Upsample2D (same call site).
+ *   x0/x1: [B, Hin, Win, C0] / [B, Hin, Win, C1] (x1 may be NULL), pixel strides ldx0 / ldx1 elements;
+ *   w    : [Cout, 3, 3, C0 + C1] bf16 (tap-major repack of the HF [Cout, Cin, 3, 3] weight);
+ *   out  : [B, Hout, Wout, Cout], Hout = Hin / stride.
+ * C0, C1 multiples of 64, Cout of 16. Epilogue flags as sb200_gemm (no GEGLU). */
+int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx0, const void* x1, int ldx1, int C0,
+                  int C1, const void* w, void* out, int ldo, int B, int Hin, int Win, int Cout,
+                  int stride, int flags, const void* bias, const void* rowbias, const void* resid,
+                  int ldr, const sb200_lora* lora, int bn);
+
+/* softmax(Q K^T * scale) V per (batch, head); head dim 64 (SDXL). Q/K/V/O are token matrices with row
+ * strides in elements; head h occupies columns [h*64, h*64+64). Replaces the attention processor called
+ * by diffusers Attention (xformers / SDPA; train_lora_xl.py:79-80).
+ *   Q: [B*Sq, ldq]  K,V: [B*Skv, ldk/ldv]  O: [B*Sq, ldo] */
+int sb200_attention(void* handle, void* stream, const void* q, int ldq, const void* k, int ldk,
+                    const void* v, int ldv, void* o, int ldo, int B, int heads, int Sq, int Skv,
+                    float scale);
+
+/* GroupNorm (+ optional SiLU) over an NHWC tensor that may be the channel concat of two sources.
+ * Replaces torch GroupNorm + SiLU in ResnetBlock2D / Transformer2DModel / conv_norm_out. */
+int sb200_groupnorm(void* handle, void* stream, const void* x0, int ldx0, int C0, const void* x1,
+                    int ldx1, int C1, const void* gamma, const void* beta, void* out, int ldo, int B,
+                    int HW, int groups, float eps, int silu, float* stats_ws);
+
+/* LayerNorm over the last dim of [M, C]. */
+int sb200_layernorm(void* handle, void* stream, const void* x, int ldx, const void* gamma,
+                    const void* beta, void* out, int ldo, int M, int C, float eps);
+
+/* Small dense layers with M <= 64 rows (time / add embeddings, time_emb_proj):
+ * out[M, N] = act_out( act_in(x)[M, K] . W[N, K]^T + bias ) (+ LoRA), act: 0 none, 1 SiLU. */
+int sb200_small_linear(void* handle, void* stream, const void* x, int ldx, const void* w, int ldw,
+                       const void* bias, void* out, int ldo, int M, int N, int K, int act_in,
+                       int act_out, const sb200_lora* lora);
+
+/* Sinusoidal embedding (diffusers get_timestep_embedding, flip_sin_to_cos=True, shift 0):
+ * out[i, :] = [cos(v_i f_j) | sin(v_i f_j)], f_j = exp(-ln(10000) j / (dim/2)); fp32 math, bf16 out. */
+int sb200_sinusoid(void* handle, void* stream, const float* values, int n, int dim, void* out, int ldo);
+
+/* conv_in: 3x3, 4 -> Cout, NCHW fp32/bf16 latent in, NHWC bf16 out. w: [Cout, 3, 3, 4]. */
+int sb200_conv_in(void* handle, void* stream, const void* latent_nchw, int latent_is_f32, const void* w,
+                  const void* bias, void* out, int B, int H, int W, int Cout);
+/* conv_out: 3x3, Cin -> 4 on an NHWC bf16 tensor (already normalised + SiLU), NCHW out (bf16 or fp32).
+ * w: [4, 3, 3, Cin]. */
+int sb200_conv_out(void* handle, void* stream, const void* x, const void* w, const void* bias, void* out,
+                   int out_is_f32, int B, int H, int W, int Cin);
+
+/* nearest-neighbour x2 upsample of an NHWC tensor (Upsample2D before its conv). */
+int sb200_upsample2x(void* handle, void* stream, const void* x, void* out, int B, int H, int W, int C);
+
+/* Classifier-free guidance + DDIM step on NCHW latents (train_util.py:250-253 + scheduler.step, :291):
+ *   eps = eps_u + g (eps_c - eps_u);  x0 = (x - sqrt(1-a_t) eps) / sqrt(a_t);
+ *   x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps.
+ * eps2 holds the unconditional batch followed by the conditional batch (n elements each). If x is NULL
+ * only the guided eps is written to eps_out. */
+int sb200_cfg_ddim(void* handle, void* stream, const void* eps2, int eps_is_f32, float g, const void* x,
+                   float a_t, float a_prev, void* x_prev, void* eps_out, int out_is_f32, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SB200_H_ */
