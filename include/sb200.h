@@ -55,7 +55,9 @@ int sb200_destroy(void* handle);
  *   up   : [N, r] bf16 (lora_up.weight); output column n uses down rows [(n / group_n) * r, +r), so one call
  *          can carry several adapted leaves that share an input (to_q|to_k|to_v fused: group_n = C).
  *   scale: multiplier * alpha / rank, a run-time scalar (the slider value changes per denoise step,
- *          eval-scripts/generate_images_xl.py:327-330). */
+ *          eval-scripts/generate_images_xl.py:327-330).
+ *   scale_dev: optional device pointer to one float multiplied into scale when the kernel runs, so a
+ *          captured CUDA graph can be replayed with a different slider value (NULL = unused). */
 typedef struct sb200_lora {
   const void* down;
   const void* up;
@@ -63,6 +65,7 @@ typedef struct sb200_lora {
   int rt;
   int group_n;
   float scale;
+  const float* scale_dev;
 } sb200_lora;
 
 /* out[M, N] = epilogue( X[M, K] . W[N, K]^T )  — every nn.Linear on the path and the 1x1 conv_shortcut.
@@ -106,10 +109,11 @@ int sb200_layernorm(void* handle, void* stream, const void* x, int ldx, const vo
                     const void* beta, void* out, int ldo, int M, int C, float eps);
 
 /* Small dense layers with M <= 64 rows (time / add embeddings, time_emb_proj):
- * out[M, N] = act_out( act_in(x)[M, K] . W[N, K]^T + bias ) (+ LoRA), act: 0 none, 1 SiLU. */
+ * out[M, N] = act_out( act_in(x)[M, K] . W[N, K]^T + bias (+ LoRA) ) + resid[M, N], act: 0 none, 1 SiLU;
+ * resid (row stride N) may be NULL. */
 int sb200_small_linear(void* handle, void* stream, const void* x, int ldx, const void* w, int ldw,
                        const void* bias, void* out, int ldo, int M, int N, int K, int act_in,
-                       int act_out, const sb200_lora* lora);
+                       int act_out, const sb200_lora* lora, const void* resid);
 
 /* Sinusoidal embedding (diffusers get_timestep_embedding, flip_sin_to_cos=True, shift 0):
  * out[i, :] = [cos(v_i f_j) | sin(v_i f_j)], f_j = exp(-ln(10000) j / (dim/2)); fp32 math, bf16 out. */

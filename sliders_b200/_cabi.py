@@ -28,6 +28,7 @@ class LoraArgs(C.Structure):
         ("rt", C.c_int),
         ("group_n", C.c_int),
         ("scale", C.c_float),
+        ("scale_dev", C.c_void_p),
     ]
 
 
@@ -46,7 +47,7 @@ SIGNATURES = {
     "sb200_attention": [_p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _f],
     "sb200_groupnorm": [_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p],
     "sb200_layernorm": [_p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _f],
-    "sb200_small_linear": [_p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _LP],
+    "sb200_small_linear": [_p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _LP, _p],
     "sb200_sinusoid": [_p, _p, _p, _i, _i, _p, _i],
     "sb200_conv_in": [_p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i],
     "sb200_conv_out": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i],

@@ -1,0 +1,312 @@
+// Flash-attention forward for sm_100a, head dim 64:  O = softmax(Q K^T * scale) V  per (batch, head).
+//
+// One CTA per (128-query tile, head, batch); two CTAs are resident per SM (256 TMEM columns, ~81 KB smem
+// each) so one CTA's tensor-core work overlaps the other's softmax.
+//   warp 0      TMA producer: Q tile once, then K / V tiles (128 keys x 64) through 2-stage rings
+//   warp 1      MMA issuer  : S = Q K^T   (tcgen05.mma SS, 128x128x64, fp32 in TMEM columns [0,128))
+//                             O += P V    (tcgen05.mma TS: P read from TMEM, V MN-major from smem)
+//   warps 2..5  softmax     : one query row per thread. Two passes over S in TMEM (row max, then
+//                             exp2 + bf16 pack), P written back to TMEM columns [128,192) as the A
+//                             operand of the PV MMA; the O accumulator (columns [192,256)) stays in TMEM
+//                             and is rescaled lazily (only when the running max grows by > 2^8).
+// Keys beyond Skv (cross-attention: 77) are masked to -inf; TMA zero-fills the out-of-range rows.
+//
+// Replaces the attention processor that diffusers' Attention calls (xformers memory_efficient_attention /
+// torch SDPA; reference: trainscripts/textsliders/train_lora_xl.py:79-80, train_lora.py:68).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace sb200 {
+
+constexpr int kAttnThreads = 192;
+constexpr int kAttnStages = 2;
+constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kAttnSmem = kTileBytes * (1 + 2 * kAttnStages) + 1024 /*barriers*/ + 1024 /*align*/;
+constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;
+  __nv_bfloat16* o;
+  int ldo;
+  int Sq, Skv;
+  int n_kv_tiles;
+  float scale_log2;  // scale * log2(e)
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+
+  const uint32_t sQ = base;
+  const uint32_t sK = base + kTileBytes;
+  const uint32_t sV = sK + kAttnStages * kTileBytes;
+  const uint32_t bars = sV + kAttnStages * kTileBytes;
+  const uint32_t bar_q = bars;
+  const uint32_t bar_kfull = bars + 8;                       // kAttnStages
+  const uint32_t bar_kempty = bar_kfull + 8 * kAttnStages;   // kAttnStages
+  const uint32_t bar_vfull = bar_kempty + 8 * kAttnStages;
+  const uint32_t bar_vempty = bar_vfull + 8 * kAttnStages;
+  const uint32_t bar_sfull = bar_vempty + 8 * kAttnStages;
+  const uint32_t bar_sfree = bar_sfull + 8;
+  const uint32_t bar_pfull = bar_sfree + 8;
+  const uint32_t bar_pvdone = bar_pfull + 8;
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem + (bars - base) + 512);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < kAttnStages; ++i) {
+      mbar_init(bar_kfull + 8 * i, 1);
+      mbar_init(bar_kempty + 8 * i, 1);
+      mbar_init(bar_vfull + 8 * i, 1);
+      mbar_init(bar_vempty + 8 * i, 1);
+    }
+    mbar_init(bar_sfull, 1);
+    mbar_init(bar_sfree, 4);
+    mbar_init(bar_pfull, 4);
+    mbar_init(bar_pvdone, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n = p.n_kv_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, kTileBytes);
+      tma_load_3d(sQ, &p.tmQ, bar_q, head * 64, qt * 128, b);
+      for (int j = 0; j < n; ++j) {
+        const int s = j % kAttnStages;
+        const uint32_t ph = (j / kAttnStages) & 1;
+        mbar_wait(bar_kempty + 8 * s, ph ^ 1u);
+        mbar_expect_tx(bar_kfull + 8 * s, kTileBytes);
+        tma_load_3d(sK + s * kTileBytes, &p.tmK, bar_kfull + 8 * s, head * 64, j * 128, b);
+        mbar_wait(bar_vempty + 8 * s, ph ^ 1u);
+        mbar_expect_tx(bar_vfull + 8 * s, kTileBytes);
+        tma_load_3d(sV + s * kTileBytes, &p.tmV, bar_vfull + 8 * s, head * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);  // B (= V) is MN-major
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < n; ++j) {
+        const int s = j % kAttnStages;
+        const uint32_t ph = (j / kAttnStages) & 1;
+        // ---- S_j = Q K_j^T
+        mbar_wait(bar_kfull + 8 * s, ph);
+        mbar_wait(bar_sfree, (j & 1) ^ 1u);  // softmax finished reading S_{j-1}
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_ss(tmem_base + kColS, umma_desc_sw128(sQ + k * 32),
+                  umma_desc_sw128(sK + s * kTileBytes + k * 32), idesc_qk, k != 0);
+        }
+        umma_commit(bar_kempty + 8 * s);
+        umma_commit(bar_sfull);
+        // ---- O += P_j V_j
+        mbar_wait(bar_vfull + 8 * s, ph);
+        mbar_wait(bar_pfull, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          umma_ts(tmem_base + kColO, tmem_base + kColP + k * 8,
+                  umma_desc_sw128(sV + s * kTileBytes + k * 2048), idesc_pv, (j | k) != 0);
+        }
+        umma_commit(bar_vempty + 8 * s);
+        umma_commit(bar_pvdone);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / correction / store
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tl = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float m_run = -INFINITY;  // running max, already multiplied by scale*log2e
+    float l_run = 0.f;
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(bar_sfull, j & 1);
+      tc_fence_after();
+      const int kv_left = p.Skv - j * 128;  // valid keys in this tile (>= 1)
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tl + kColS + c * 32, v);
+        tmem_ld_wait();
+        if (kv_left >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      mx *= p.scale_log2;
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_run = mx;
+      } else if (mx - m_run > 8.f) {
+        need = true;
+        alpha = fast_exp2(m_run - mx);
+        m_run = mx;
+      }
+      if (j > 0) {
+        // P_{j-1} has been consumed and O holds the sum over tiles < j
+        mbar_wait(bar_pvdone, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          l_run *= alpha;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32(tl + kColO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x16(tl + kColO + c * 32, o);
+            tmem_st_x16(tl + kColO + c * 32 + 16, o + 16);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: p = exp2(s*scale*log2e - m), pack to bf16, store as the A operand of the PV MMA
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tl + kColS + c * 32, v);
+        tmem_ld_wait();
+        if (c == 3) {
+          // every S column of this row is now in registers: release S for the next QK MMA
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sfree);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_run));
+          float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_run));
+          if (c * 32 + 2 * i >= kv_left) p0 = 0.f;
+          if (c * 32 + 2 * i + 1 >= kv_left) p1 = 0.f;
+          lsum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_x16(tl + kColP + c * 16, pk);
+      }
+      l_run += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pfull);
+    }
+    // ---- finalize: O / l -> bf16 -> global
+    mbar_wait(bar_pvdone, (n - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const int srow = qt * 128 + row;
+    __nv_bfloat16* op =
+        p.o + (static_cast<size_t>(b) * p.Sq + srow) * p.ldo + head * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_x32(tl + kColO + c * 32, o);
+      tmem_ld_wait();
+      if (srow < p.Sq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" int sb200_attention(void* handle, void* stream, const void* q, int ldq, const void* k, int ldk,
+                               const void* v, int ldv, void* o, int ldo, int B, int heads, int Sq, int Skv,
+                               float scale) {
+  Ctx* ctx = as_ctx(handle);
+  SB200_REQUIRE(ctx, "attention: NULL handle");
+  SB200_REQUIRE(B > 0 && heads > 0 && Sq > 0 && Skv > 0, "attention: bad dims");
+  SB200_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+                "attention: leading dims must be multiples of 8");
+  SB200_REQUIRE(ldq >= heads * 64 && ldk >= heads * 64 && ldv >= heads * 64 && ldo >= heads * 64,
+                "attention: head dim is fixed at 64 (heads=%d needs >= %d columns)", heads, heads * 64);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  int st;
+  const uint32_t box[3] = {64, 128, 1};
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(Sq),
+                              static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(ldq) * 2 * Sq};
+    if ((st = make_tmap_bf16(ctx, &p.tmQ, q, 3, dims, strides, box))) return st;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(Skv),
+                              static_cast<uint64_t>(B)};
+    const uint64_t sk[2] = {static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(ldk) * 2 * Skv};
+    const uint64_t sv[2] = {static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(ldv) * 2 * Skv};
+    if ((st = make_tmap_bf16(ctx, &p.tmK, k, 3, dims, sk, box))) return st;
+    if ((st = make_tmap_bf16(ctx, &p.tmV, v, 3, dims, sv, box))) return st;
+  }
+  p.o = static_cast<__nv_bfloat16*>(o);
+  p.ldo = ldo;
+  p.Sq = Sq;
+  p.Skv = Skv;
+  p.n_kv_tiles = (Skv + 127) / 128;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  if (!ctx->attn_attr_set) {
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kAttnSmem));
+    ctx->attn_attr_set = true;
+  }
+  dim3 grid((Sq + 127) / 128, heads, B);
+  attention_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  SB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -59,6 +59,7 @@ struct GemmParams {
   const __nv_bfloat16* lora_up;
   int lora_r, lora_rt, lora_group_n;
   float lora_scale;
+  const float* lora_scale_dev;
 };
 
 template <int R>
@@ -248,6 +249,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
               : nullptr;
       float tl[8];
       int cur_group = -1;
+      const float lscale =
+          has_lora ? (p.lora_scale_dev ? p.lora_scale * __ldg(p.lora_scale_dev) : p.lora_scale) : 0.f;
       for (int c = 0; c < p.ncols_out; c += 16) {
         const int n = n_base + c;
         if (n >= p.Nout) break;  // warp-uniform
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             tmem_ld_x8(taddr + p.bn + grp * p.lora_r, tv);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tl[j] = __uint_as_float(tv[j]) * p.lora_scale;
+            for (int j = 0; j < 8; ++j) tl[j] = __uint_as_float(tv[j]) * lscale;
           }
         }
         tmem_ld_wait();
@@ -456,6 +459,7 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
     p.lora_rt = lora->rt;
     p.lora_group_n = lora->group_n;
     p.lora_scale = lora->scale;
+    p.lora_scale_dev = lora->scale_dev;
   }
   const int step = geglu ? 32 : 16;
   if (bn <= 0) {
@@ -568,6 +572,7 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
     p.lora_rt = lora->rt;
     p.lora_group_n = lora->group_n;
     p.lora_scale = lora->scale;
+    p.lora_scale_dev = lora->scale_dev;
   }
   if (bn <= 0) bn = pick_bn(p.num_m_tiles, Cout, max_bn, 16, ctx->num_sms, p.kblocks);
   SB200_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= max_bn, "conv3x3: bn=%d invalid", bn);

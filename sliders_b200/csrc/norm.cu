@@ -1,0 +1,284 @@
+// GroupNorm(+SiLU) and LayerNorm for channels-last bf16 activations (HBM-bound kernels: 16-byte vector
+// loads, fp32 statistics, warp-shuffle / shared-memory reductions).
+//
+// Replaces torch.nn.GroupNorm + SiLU in diffusers ResnetBlock2D / Transformer2DModel / conv_norm_out and
+// torch.nn.LayerNorm in BasicTransformerBlock (called under trainscripts/textsliders/train_util.py:242-247).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace sb200 {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[b][g] = {sum, sumsq} over (HW x C/G) elements; the input may be the
+// channel concat of two NHWC sources.
+// grid (chunks, B); block = (C/8) * rows_par threads: thread (r, cv) owns channel vector cv and walks
+// rows r, r + rows_par, ... of its chunk.
+// ------------------------------------------------------------------------------------------------
+struct GnArgs {
+  const __nv_bfloat16* x0;
+  const __nv_bfloat16* x1;
+  int ld0, ld1, C0, C;
+  int HW, groups, cpg;
+  int rows_per_block;
+};
+
+__global__ void gn_stats_kernel(GnArgs a, float* __restrict__ stats) {
+  extern __shared__ float sh[];  // [2 * groups]
+  const int nvec = a.C >> 3;
+  const int cv = threadIdx.x % nvec;
+  const int r0 = threadIdx.x / nvec;
+  const int rows_par = blockDim.x / nvec;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int c = cv << 3;
+  const __nv_bfloat16* src;
+  int ld, cc;
+  if (c < a.C0) {
+    src = a.x0, ld = a.ld0, cc = c;
+  } else {
+    src = a.x1, ld = a.ld1, cc = c - a.C0;
+  }
+  const int row_begin = blockIdx.x * a.rows_per_block;
+  const int row_end = min(row_begin + a.rows_per_block, a.HW);
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+  if (r0 < rows_par) {
+    for (int r = row_begin + r0; r < row_end; r += rows_par) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(b) * a.HW + r) * ld + cc));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float lo = bf16_lo(w[i]), hi = bf16_hi(w[i]);
+        s[2 * i] += lo;
+        ss[2 * i] += lo * lo;
+        s[2 * i + 1] += hi;
+        ss[2 * i + 1] += hi * hi;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / a.cpg;
+      atomicAdd(&sh[2 * g], s[i]);
+      atomicAdd(&sh[2 * g + 1], ss[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x)
+    atomicAdd(&stats[static_cast<size_t>(b) * 2 * a.groups + i], sh[i]);
+}
+
+struct GnApplyArgs {
+  GnArgs in;
+  const __nv_bfloat16* gamma;
+  const __nv_bfloat16* beta;
+  __nv_bfloat16* out;
+  int ldo;
+  int B;
+  float eps;
+  int silu;
+};
+
+__global__ void gn_apply_kernel(GnApplyArgs a, const float* __restrict__ stats) {
+  const GnArgs& in = a.in;
+  const int nvec = in.C >> 3;
+  const size_t total = static_cast<size_t>(a.B) * in.HW * nvec;
+  const float inv_n = 1.f / (static_cast<float>(in.HW) * in.cpg);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % nvec);
+    const size_t pix = idx / nvec;  // b * HW + r
+    const int b = static_cast<int>(pix / in.HW);
+    const int c = cv << 3;
+    const __nv_bfloat16* src;
+    int ld, cc;
+    if (c < in.C0) {
+      src = in.x0, ld = in.ld0, cc = c;
+    } else {
+      src = in.x1, ld = in.ld1, cc = c - in.C0;
+    }
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + pix * ld + cc));
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(a.gamma + c));
+    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(a.beta + c));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = bf16_lo(w[i]);
+      f[2 * i + 1] = bf16_hi(w[i]);
+    }
+    const float* st = stats + static_cast<size_t>(b) * 2 * in.groups;
+    int g_prev = -1;
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / in.cpg;
+      if (g != g_prev) {
+        g_prev = g;
+        mean = st[2 * g] * inv_n;
+        const float var = fmaxf(st[2 * g + 1] * inv_n - mean * mean, 0.f);
+        rstd = rsqrtf(var + a.eps);
+      }
+      const float gm = (i & 1) ? bf16_hi(gw[i >> 1]) : bf16_lo(gw[i >> 1]);
+      const float bt = (i & 1) ? bf16_hi(bw[i >> 1]) : bf16_lo(bw[i >> 1]);
+      float y = (f[i] - mean) * rstd * gm + bt;
+      if (a.silu) y = silu_f(y);
+      f[i] = y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(a.out + pix * a.ldo + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers between the mean and variance passes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 8;  // C <= 8 * 32 * 8 = 2048
+
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                 const __nv_bfloat16* __restrict__ gamma,
+                                 const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                 int ldo, int M, int C, float eps) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
+       row += gridDim.x * warps_per_block) {
+    const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ldx;
+    float f[kLnMaxVec][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int v = lane + k * 32;
+      if (v < nvec) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f[k][2 * i] = bf16_lo(w[i]);
+          f[k][2 * i + 1] = bf16_hi(w[i]);
+          sum += f[k][2 * i] + f[k][2 * i + 1];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      if (lane + k * 32 < nvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = f[k][i] - mean;
+          var += d * d;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / C + eps);
+    __nv_bfloat16* orow = out + static_cast<size_t>(row) * ldo;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int v = lane + k * 32;
+      if (v < nvec) {
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + v * 8));
+        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + v * 8));
+        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float y0 = (f[k][2 * i] - mean) * rstd * bf16_lo(gw[i]) + bf16_lo(bw[i]);
+          const float y1 = (f[k][2 * i + 1] - mean) * rstd * bf16_hi(gw[i]) + bf16_hi(bw[i]);
+          o[i] = pack_bf16x2(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(orow + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" int sb200_groupnorm(void* handle, void* stream, const void* x0, int ldx0, int C0, const void* x1,
+                               int ldx1, int C1, const void* gamma, const void* beta, void* out, int ldo,
+                               int B, int HW, int groups, float eps, int silu, float* stats_ws) {
+  Ctx* ctx = as_ctx(handle);
+  SB200_REQUIRE(ctx, "groupnorm: NULL handle");
+  if (!x1) C1 = 0;
+  const int C = C0 + C1;
+  SB200_REQUIRE(B > 0 && HW > 0 && C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0, "groupnorm: dims (C0=%d C1=%d)", C0, C1);
+  SB200_REQUIRE(groups > 0 && C % groups == 0, "groupnorm: C=%d not divisible by groups=%d", C, groups);
+  SB200_REQUIRE(ldx0 % 8 == 0 && ldo % 8 == 0 && (C1 == 0 || ldx1 % 8 == 0), "groupnorm: leading dims");
+  SB200_REQUIRE(C / 8 <= 1024, "groupnorm: C=%d too large", C);
+  SB200_REQUIRE(stats_ws && gamma && beta, "groupnorm: NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GnArgs a;
+  a.x0 = static_cast<const __nv_bfloat16*>(x0);
+  a.x1 = static_cast<const __nv_bfloat16*>(x1);
+  a.ld0 = ldx0;
+  a.ld1 = ldx1;
+  a.C0 = C0;
+  a.C = C;
+  a.HW = HW;
+  a.groups = groups;
+  a.cpg = C / groups;
+  const int nvec = C / 8;
+  int rows_par = 512 / nvec;
+  if (rows_par < 1) rows_par = 1;
+  const int threads = nvec * rows_par;
+  // enough blocks to fill the machine, but each block should walk >= 8 rows per thread
+  int chunks = (ctx->num_sms * 4 + B - 1) / B;
+  int rows_per_block = (HW + chunks - 1) / chunks;
+  const int min_rows = rows_par * 8;
+  if (rows_per_block < min_rows) rows_per_block = min_rows;
+  chunks = (HW + rows_per_block - 1) / rows_per_block;
+  a.rows_per_block = rows_per_block;
+  SB200_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * B, s));
+  gn_stats_kernel<<<dim3(chunks, B), threads, sizeof(float) * 2 * groups, s>>>(a, stats_ws);
+  SB200_CUDA_CHECK(cudaGetLastError());
+  GnApplyArgs ap;
+  ap.in = a;
+  ap.gamma = static_cast<const __nv_bfloat16*>(gamma);
+  ap.beta = static_cast<const __nv_bfloat16*>(beta);
+  ap.out = static_cast<__nv_bfloat16*>(out);
+  ap.ldo = ldo;
+  ap.B = B;
+  ap.eps = eps;
+  ap.silu = silu;
+  const size_t total = static_cast<size_t>(B) * HW * nvec;
+  int blocks = static_cast<int>((total + 255) / 256);
+  const int max_blocks = ctx->num_sms * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  gn_apply_kernel<<<blocks, 256, 0, s>>>(ap, stats_ws);
+  SB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sb200_layernorm(void* handle, void* stream, const void* x, int ldx, const void* gamma,
+                               const void* beta, void* out, int ldo, int M, int C, float eps) {
+  Ctx* ctx = as_ctx(handle);
+  SB200_REQUIRE(ctx, "layernorm: NULL handle");
+  SB200_REQUIRE(M > 0 && C > 0 && C % 8 == 0 && C <= kLnMaxVec * 256, "layernorm: C=%d unsupported", C);
+  SB200_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0, "layernorm: leading dims");
+  const int warps = 8;
+  int blocks = (M + warps - 1) / warps;
+  const int max_blocks = ctx->num_sms * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  layernorm_kernel<<<blocks, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(gamma),
+      static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(out), ldo, M, C, eps);
+  SB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

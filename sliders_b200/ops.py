@@ -1,0 +1,220 @@
+"""Thin torch-tensor wrappers over the C ABI (include/sb200.h).  Every function enqueues exactly the
+kernels named in its docstring on torch's *current* stream, so the whole UNet forward can be captured in a
+CUDA graph.  There is deliberately no PyTorch fallback: a missing extension or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _cabi
+from ._cabi import EPI_BIAS, EPI_GEGLU, EPI_LORA, EPI_RESID, EPI_ROWBIAS, LoraArgs
+
+BF16 = torch.bfloat16
+
+# launches issued through this module since import (bench.py reports it as gpu_launches)
+launch_count = 0
+_KERNELS_PER_CALL = {"groupnorm": 3}  # memset + stats + apply
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ctx(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _cabi.Sb200Error("sliders_b200 kernels need CUDA tensors on a B200 (no CPU fallback)")
+    return _cabi.handle(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _count(name: str = "") -> None:
+    global launch_count
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
+
+
+class Lora:
+    """Packed LoRA side inputs of one fused GEMM/conv call (see struct sb200_lora)."""
+
+    __slots__ = ("down", "up", "r", "rt", "group_n", "scale", "scale_dev", "_c")
+
+    def __init__(self, down: torch.Tensor, up: torch.Tensor, r: int, group_n: int, scale: float,
+                 scale_dev: Optional[torch.Tensor] = None):
+        self.down, self.up, self.r, self.rt, self.group_n = down, up, r, down.shape[0], group_n
+        self.scale, self.scale_dev = float(scale), scale_dev
+        self._c = LoraArgs(down.data_ptr(), up.data_ptr(), r, self.rt, group_n, self.scale,
+                           scale_dev.data_ptr() if scale_dev is not None else None)
+
+    def ref(self):
+        return C.byref(self._c)
+
+
+def gemm(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowbias=None, rows_per_batch: int = 1, resid=None,
+         geglu: bool = False, lora: Optional[Lora] = None, x1: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, bn: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue([x | x1] @ w.T): one tcgen05 `gemm_kernel` launch."""
+    M, K0 = x.shape
+    N, K = w.shape
+    flags = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+    if rowbias is not None:
+        flags |= EPI_ROWBIAS
+    if resid is not None:
+        flags |= EPI_RESID
+    if geglu:
+        flags |= EPI_GEGLU
+    if lora is not None:
+        flags |= EPI_LORA
+    nout = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, nout), device=x.device, dtype=BF16)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_gemm(
+        _ctx(x), _stream(), _p(x), x.stride(0), _p(x1), x1.stride(0) if x1 is not None else 0, K0,
+        _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, flags, _p(bias), _p(rowbias), rows_per_batch,
+        _p(resid), resid.stride(0) if resid is not None else 0, lora.ref() if lora is not None else None, bn))
+    _count()
+    return out
+
+
+def conv3x3(x0: torch.Tensor, w_packed: torch.Tensor, *, x1: Optional[torch.Tensor] = None, stride: int = 1,
+            bias=None, rowbias=None, resid=None, lora: Optional[Lora] = None, bn: int = 0) -> torch.Tensor:
+    """3x3 / pad 1 conv on NHWC bf16 ([B,H,W,C] tensors); w_packed is [Cout,3,3,Cin].  One `gemm_kernel`."""
+    B, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    Cout = w_packed.shape[0]
+    flags = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+    if rowbias is not None:
+        flags |= EPI_ROWBIAS
+    if resid is not None:
+        flags |= EPI_RESID
+    if lora is not None:
+        flags |= EPI_LORA
+    out = torch.empty((B, H // stride, W // stride, Cout), device=x0.device, dtype=BF16)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_conv3x3(
+        _ctx(x0), _stream(), _p(x0), x0.stride(2), _p(x1), x1.stride(2) if x1 is not None else 0, C0, C1,
+        _p(w_packed), _p(out), Cout, B, H, W, Cout, stride, flags, _p(bias), _p(rowbias), _p(resid),
+        resid.stride(2) if resid is not None else 0, lora.ref() if lora is not None else None, bn))
+    _count()
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, Sq: int, Skv: int,
+              scale: float) -> torch.Tensor:
+    """q/k/v: 2-D (possibly column-sliced) token matrices, head dim 64.  One `attention_kernel`."""
+    out = torch.empty((B * Sq, heads * 64), device=q.device, dtype=BF16)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_attention(_ctx(q), _stream(), _p(q), q.stride(0), _p(k), k.stride(0), _p(v),
+                                    v.stride(0), _p(out), out.stride(0), B, heads, Sq, Skv, float(scale)))
+    _count()
+    return out
+
+
+def groupnorm(x0: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool, *,
+              x1: Optional[torch.Tensor] = None, stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x0/x1: [B, HW, C] (or [B,H,W,C]) NHWC; returns the concatenated, normalised tensor."""
+    shp = x0.shape
+    B, C0 = shp[0], shp[-1]
+    HW = x0.numel() // (B * C0)
+    C1 = x1.shape[-1] if x1 is not None else 0
+    out = torch.empty(shp[:-1] + (C0 + C1,), device=x0.device, dtype=BF16)
+    if stats_ws is None:
+        stats_ws = torch.empty(B * groups * 2, device=x0.device, dtype=torch.float32)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_groupnorm(_ctx(x0), _stream(), _p(x0), x0.stride(-2), C0, _p(x1),
+                                    x1.stride(-2) if x1 is not None else 0, C1, _p(gamma), _p(beta), _p(out),
+                                    C0 + C1, B, HW, groups, float(eps), int(silu), _p(stats_ws)))
+    _count("groupnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
+    M, Cc = x.shape
+    out = torch.empty((M, Cc), device=x.device, dtype=BF16)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_layernorm(_ctx(x), _stream(), _p(x), x.stride(0), _p(gamma), _p(beta), _p(out), Cc, M,
+                                    Cc, float(eps)))
+    _count()
+    return out
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias=None, *, act_in: bool = False, act_out: bool = False,
+                 lora: Optional[Lora] = None, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), device=x.device, dtype=BF16)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_small_linear(_ctx(x), _stream(), _p(x), x.stride(0), _p(w), w.stride(0), _p(bias),
+                                       _p(out), N, M, N, K, int(act_in), int(act_out),
+                                       lora.ref() if lora is not None else None, _p(resid)))
+    _count()
+    return out
+
+
+def sinusoid(values: torch.Tensor, dim: int) -> torch.Tensor:
+    """values: fp32 [n] on device -> [n, dim] bf16 ([cos | sin])."""
+    n = values.numel()
+    out = torch.empty((n, dim), device=values.device, dtype=BF16)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_sinusoid(_ctx(values), _stream(), _p(values), n, dim, _p(out), dim))
+    _count()
+    return out
+
+
+def conv_in(latent: torch.Tensor, w_packed: torch.Tensor, bias) -> torch.Tensor:
+    """latent: NCHW fp32 or bf16 -> NHWC bf16 [B,H,W,Cout]."""
+    B, Cc, H, W = latent.shape
+    assert Cc == 4 and latent.is_contiguous()
+    Cout = w_packed.shape[0]
+    out = torch.empty((B, H, W, Cout), device=latent.device, dtype=BF16)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_conv_in(_ctx(latent), _stream(), _p(latent), int(latent.dtype == torch.float32),
+                                  _p(w_packed), _p(bias), _p(out), B, H, W, Cout))
+    _count()
+    return out
+
+
+def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias, out_dtype=BF16) -> torch.Tensor:
+    B, H, W, Cin = x.shape
+    out = torch.empty((B, 4, H, W), device=x.device, dtype=out_dtype)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_conv_out(_ctx(x), _stream(), _p(x), _p(w_packed), _p(bias), _p(out),
+                                   int(out_dtype == torch.float32), B, H, W, Cin))
+    _count()
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, Cc), device=x.device, dtype=BF16)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_upsample2x(_ctx(x), _stream(), _p(x), _p(out), B, H, W, Cc))
+    _count()
+    return out
+
+
+def cfg_ddim(eps2: torch.Tensor, guidance: float, x: Optional[torch.Tensor] = None, a_t: float = 1.0,
+             a_prev: float = 1.0, out_dtype=None):
+    """eps2 = [uncond batch ; cond batch] (contiguous).  Returns (guided_eps, x_prev or None)."""
+    n = eps2.numel() // 2
+    out_dtype = out_dtype or (x.dtype if x is not None else eps2.dtype)
+    shape = (eps2.shape[0] // 2,) + tuple(eps2.shape[1:])
+    eps_out = torch.empty(shape, device=eps2.device, dtype=out_dtype)
+    x_prev = torch.empty(shape, device=eps2.device, dtype=out_dtype) if x is not None else None
+    if x is not None and x.dtype != out_dtype:
+        x = x.to(out_dtype)
+    lib = _cabi.load()
+    _cabi.check(lib.sb200_cfg_ddim(_ctx(eps2), _stream(), _p(eps2), int(eps2.dtype == torch.float32),
+                                   float(guidance), _p(x), float(a_t), float(a_prev), _p(x_prev), _p(eps_out),
+                                   int(out_dtype == torch.float32), n))
+    _count()
+    return eps_out, x_prev

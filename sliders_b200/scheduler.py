@@ -1,0 +1,113 @@
+"""DDIM scheduler with the call surface the reference uses on diffusers' `DDIMScheduler`
+(constructed at trainscripts/textsliders/model_util.py:237-246: scaled_linear betas 0.00085..0.012, 1000 train
+steps, clip_sample=False, epsilon prediction; defaults otherwise: set_alpha_to_one=True, steps_offset=0,
+timestep_spacing="leading", eta=0).
+
+Used as: `scheduler.set_timesteps(n, device=…)`, `scheduler.timesteps[i]`, `scheduler.init_noise_sigma`,
+`scheduler.scale_model_input(x, t)`, `scheduler.step(eps, t, x).prev_sample`, `scheduler.add_noise(x0, n, t)`
+(train_lora_xl.py:164-233, train_util.py:156,193,234,291; imagesliders/train_util.py:201-235).
+On CUDA tensors `step` runs the fused `cfg_ddim_kernel` (ops.cfg_ddim); scalar coefficient look-ups stay on the host.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class DDIMSchedulerOutput(SimpleNamespace):
+    pass
+
+
+class DDIMScheduler:
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 beta_schedule: str = "scaled_linear", clip_sample: bool = False, set_alpha_to_one: bool = True,
+                 steps_offset: int = 0, prediction_type: str = "epsilon"):
+        if beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        elif beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        else:
+            raise NotImplementedError(beta_schedule)
+        if prediction_type != "epsilon":
+            raise NotImplementedError("only epsilon prediction is on the slider path (model_util.py:126)")
+        if clip_sample:
+            raise NotImplementedError("clip_sample=True is not used by the reference (model_util.py:243)")
+        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, beta_start=beta_start,
+                                      beta_end=beta_end, beta_schedule=beta_schedule, clip_sample=clip_sample,
+                                      set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset,
+                                      prediction_type=prediction_type)
+        self.betas = betas
+        self.alphas = 1.0 - betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self._acp = self.alphas_cumprod.double().tolist()  # host copy for scalar look-ups
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device: Union[str, torch.device, None] = None):
+        if num_inference_steps > self.config.num_train_timesteps:
+            raise ValueError("num_inference_steps exceeds num_train_timesteps")
+        self.num_inference_steps = num_inference_steps
+        step_ratio = self.config.num_train_timesteps // num_inference_steps  # "leading" spacing
+        ts = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
+        ts += self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts).to(device)
+
+    def _alphas_for(self, timestep) -> tuple:
+        t = int(timestep)
+        prev = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self._acp[t]
+        a_prev = self._acp[prev] if prev >= 0 else float(self.final_alpha_cumprod)
+        return a_t, a_prev
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, eta: float = 0.0,
+             return_dict: bool = True, **unused):
+        if self.num_inference_steps is None:
+            raise ValueError("call set_timesteps first")
+        if eta != 0.0:
+            raise NotImplementedError("eta > 0 is not used by the reference")
+        a_t, a_prev = self._alphas_for(timestep)
+        if model_output.is_cuda:
+            _, prev = ops.cfg_ddim(model_output.contiguous(), 0.0, sample.contiguous(), a_t, a_prev,
+                                   out_dtype=sample.dtype if sample.dtype in (torch.float32, torch.bfloat16)
+                                   else torch.float32, single=True)
+            prev = prev.to(sample.dtype)
+        else:  # host tensors (scheduler unit tests); not a model path
+            x0 = (sample - (1 - a_t) ** 0.5 * model_output) / a_t ** 0.5
+            prev = a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * model_output
+        if not return_dict:
+            return (prev,)
+        return DDIMSchedulerOutput(prev_sample=prev)
+
+    def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps) -> torch.Tensor:
+        acp = self.alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
+        timesteps = torch.as_tensor(timesteps, device=original_samples.device).reshape(-1)
+        sa = acp[timesteps] ** 0.5
+        sb = (1 - acp[timesteps]) ** 0.5
+        while sa.dim() < original_samples.dim():
+            sa, sb = sa.unsqueeze(-1), sb.unsqueeze(-1)
+        return sa * original_samples + sb * noise
+
+    def __len__(self):
+        return self.config.num_train_timesteps
+
+
+def create_noise_scheduler(scheduler_name: str = "ddim", prediction_type: str = "epsilon") -> DDIMScheduler:
+    """model_util.create_noise_scheduler (model_util.py:230-278); only the DDIM branch is on the hot path."""
+    name = scheduler_name.lower().replace(" ", "_")
+    if name != "ddim":
+        raise NotImplementedError(f"scheduler {scheduler_name}: sliders_b200 restates DDIM (the shipped configs' "
+                                  "choice, data/config-xl.yaml); DDPM/LMS/Euler-a are SURVEY.md §8f rank 3")
+    return DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                         num_train_timesteps=1000, clip_sample=False, prediction_type=prediction_type)

@@ -1,0 +1,672 @@
+"""B200-native replacement for the `unet(...)` call of the reference slider trainers / samplers.
+
+`UNet2DConditionModel` here is NOT the diffusers network: it is a parameter container whose module tree,
+attribute names and class names mirror diffusers 0.20.2 exactly (so that `LoRANetwork.create_modules`,
+reference trainscripts/textsliders/lora.py:164-218, discovers the same 346 / 150 leaves and writes the same
+checkpoint keys, and so that Hugging Face `unet/diffusion_pytorch_model.safetensors` state dicts load with
+`load_state_dict`), plus a forward that runs entirely in the hand-written sm_100a kernels of libsb200.so
+(ops.py).  None of the leaf modules' own `forward`s are ever executed.
+
+Call-site compatibility (reference): `unet(sample, timestep, encoder_hidden_states=…,
+added_cond_kwargs={"text_embeds", "time_ids"}).sample` — trainscripts/textsliders/train_util.py:159-163,
+242-247; eval-scripts/generate_images_xl.py:339-346 (`return_dict=False`).
+
+Data layout on the device: activations are bf16 channels-last token matrices [B*H*W, C]; frozen weights are
+bf16, Linear in HF [out, in] layout (already the K-major B operand), Conv2d 3x3 repacked once to
+[Cout, 3, 3, Cin] (tap-major K), to_q|to_k|to_v fused to one [3C, C] matrix, attn2 to_k|to_v to [2C, Dctx].
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import BF16, Lora
+
+
+# --------------------------------------------------------------------------------------------------
+# configuration (same fields as the diffusers config.json entries that matter for the architecture)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class UNetConfig:
+    in_channels: int = 4
+    out_channels: int = 4
+    sample_size: int = 64
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
+    down_block_types: Tuple[str, ...] = ("CrossAttnDownBlock2D",) * 3 + ("DownBlock2D",)
+    up_block_types: Tuple[str, ...] = ("UpBlock2D",) + ("CrossAttnUpBlock2D",) * 3
+    layers_per_block: int = 2
+    transformer_layers_per_block: Tuple[int, ...] = (1, 1, 1, 1)
+    attention_head_dim: Tuple[int, ...] = (8, 8, 8, 8)  # diffusers naming quirk: number of heads per level
+    cross_attention_dim: int = 768
+    use_linear_projection: bool = False
+    addition_embed_type: Optional[str] = None
+    addition_time_embed_dim: Optional[int] = None
+    projection_class_embeddings_input_dim: Optional[int] = None
+    norm_num_groups: int = 32
+    norm_eps: float = 1e-5
+
+    @staticmethod
+    def sdxl() -> "UNetConfig":
+        return UNetConfig(sample_size=128, block_out_channels=(320, 640, 1280),
+                          down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+                          up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"),
+                          transformer_layers_per_block=(1, 2, 10), attention_head_dim=(5, 10, 20),
+                          cross_attention_dim=2048, use_linear_projection=True, addition_embed_type="text_time",
+                          addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816)
+
+    @staticmethod
+    def sd15() -> "UNetConfig":
+        return UNetConfig()
+
+    @staticmethod
+    def from_dict(d: dict) -> "UNetConfig":
+        known = {k: (tuple(v) if isinstance(v, list) else v) for k, v in d.items()
+                 if k in UNetConfig.__dataclass_fields__}
+        cfg = UNetConfig(**known)
+        n = len(cfg.block_out_channels)
+        for f in ("transformer_layers_per_block", "attention_head_dim"):
+            v = getattr(cfg, f)
+            if isinstance(v, int):
+                setattr(cfg, f, (v,) * n)
+        return cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers — class names are load-bearing (lora.py matches on __class__.__name__)
+# --------------------------------------------------------------------------------------------------
+class _Container(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - never executed by design
+        raise RuntimeError(f"{type(self).__name__} is a parameter container; the forward runs in "
+                           "sliders_b200 kernels via UNet2DConditionModel.forward")
+
+
+class Timesteps(_Container):
+    def __init__(self, num_channels: int):
+        super().__init__()
+        self.num_channels = num_channels
+
+
+class TimestepEmbedding(_Container):
+    def __init__(self, in_channels: int, time_embed_dim: int):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.act = nn.SiLU()
+        self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+
+
+class Attention(_Container):
+    def __init__(self, query_dim: int, cross_attention_dim: Optional[int], heads: int, dim_head: int):
+        super().__init__()
+        inner = heads * dim_head
+        ctx = query_dim if cross_attention_dim is None else cross_attention_dim
+        self.heads, self.dim_head, self.is_cross = heads, dim_head, cross_attention_dim is not None
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(ctx, inner, bias=False)
+        self.to_v = nn.Linear(ctx, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+
+
+class GEGLU(_Container):
+    def __init__(self, dim_in: int, dim_out: int):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(_Container):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+
+class BasicTransformerBlock(_Container):
+    def __init__(self, dim: int, heads: int, dim_head: int, cross_attention_dim: int):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, cross_attention_dim, heads, dim_head)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+
+class Transformer2DModel(_Container):
+    def __init__(self, heads: int, dim_head: int, in_channels: int, num_layers: int, cross_attention_dim: int,
+                 groups: int, use_linear_projection: bool):
+        super().__init__()
+        inner = heads * dim_head
+        self.use_linear_projection = use_linear_projection
+        self.norm = nn.GroupNorm(groups, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner) if use_linear_projection else nn.Conv2d(in_channels, inner, 1)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner, heads, dim_head, cross_attention_dim) for _ in range(num_layers)])
+        self.proj_out = nn.Linear(inner, in_channels) if use_linear_projection else nn.Conv2d(inner, in_channels, 1)
+
+
+class ResnetBlock2D(_Container):
+    def __init__(self, in_channels: int, out_channels: int, temb_channels: int, groups: int, eps: float):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, 1, 1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels)
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps, affine=True)
+        self.dropout = nn.Dropout(0.0)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, 1, 1)
+        self.nonlinearity = nn.SiLU()
+        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
+
+
+class Downsample2D(_Container):
+    def __init__(self, channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
+
+
+class Upsample2D(_Container):
+    def __init__(self, channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+
+
+def _resnets_for_up(in_channels, prev_output_channel, out_channels, temb, n, groups, eps):
+    blocks = []
+    for i in range(n):
+        skip = in_channels if i == n - 1 else out_channels
+        rin = prev_output_channel if i == 0 else out_channels
+        blocks.append(ResnetBlock2D(rin + skip, out_channels, temb, groups, eps))
+    return blocks
+
+
+class DownBlock2D(_Container):
+    def __init__(self, cin, cout, temb, n, groups, eps, add_downsample):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb, groups, eps) for i in range(n)])
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_downsample else None
+
+
+class CrossAttnDownBlock2D(_Container):
+    def __init__(self, cin, cout, temb, n, tlayers, heads, ctx_dim, groups, eps, add_downsample, linear_proj):
+        super().__init__()
+        self.attentions = nn.ModuleList(
+            [Transformer2DModel(heads, cout // heads, cout, tlayers, ctx_dim, groups, linear_proj) for _ in range(n)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb, groups, eps) for i in range(n)])
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_downsample else None
+
+
+class UNetMidBlock2DCrossAttn(_Container):
+    def __init__(self, c, temb, tlayers, heads, ctx_dim, groups, eps, linear_proj):
+        super().__init__()
+        self.attentions = nn.ModuleList([Transformer2DModel(heads, c // heads, c, tlayers, ctx_dim, groups, linear_proj)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(c, c, temb, groups, eps), ResnetBlock2D(c, c, temb, groups, eps)])
+
+
+class UpBlock2D(_Container):
+    def __init__(self, cin, prev, cout, temb, n, groups, eps, add_upsample):
+        super().__init__()
+        self.resnets = nn.ModuleList(_resnets_for_up(cin, prev, cout, temb, n, groups, eps))
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_upsample else None
+
+
+class CrossAttnUpBlock2D(_Container):
+    def __init__(self, cin, prev, cout, temb, n, tlayers, heads, ctx_dim, groups, eps, add_upsample, linear_proj):
+        super().__init__()
+        self.attentions = nn.ModuleList(
+            [Transformer2DModel(heads, cout // heads, cout, tlayers, ctx_dim, groups, linear_proj) for _ in range(n)])
+        self.resnets = nn.ModuleList(_resnets_for_up(cin, prev, cout, temb, n, groups, eps))
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_upsample else None
+
+
+class UNet2DConditionOutput(SimpleNamespace):
+    """`.sample` holder, like diffusers' BaseOutput (train_util.py:163)."""
+
+
+# --------------------------------------------------------------------------------------------------
+# LoRA discovery: both the reference lora.py and sliders_b200.lora replace `leaf.forward` by a bound method
+# of the adaptor module (lora.py:103-106), which is how the engine finds the adaptor of a leaf.
+# --------------------------------------------------------------------------------------------------
+def _adaptor_of(leaf: nn.Module):
+    fwd = leaf.__dict__.get("forward")
+    owner = getattr(fwd, "__self__", None)
+    if owner is not None and hasattr(owner, "lora_down") and hasattr(owner, "lora_up"):
+        return owner
+    return None
+
+
+class _LoraPack:
+    """Packed (down [rt,K], up [N,r]) buffers of one fused call site; repacked only when a parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.down = None
+        self.up = None
+
+
+class UNet2DConditionModel(nn.Module):
+    """Drop-in for the diffusers model at the reference call sites (see module docstring)."""
+
+    def __init__(self, config: UNetConfig):
+        super().__init__()
+        c = config
+        self.config = SimpleNamespace(**c.__dict__)
+        boc = c.block_out_channels
+        temb = boc[0] * 4
+        self.conv_in = nn.Conv2d(c.in_channels, boc[0], 3, padding=1)
+        self.time_proj = Timesteps(boc[0])
+        self.time_embedding = TimestepEmbedding(boc[0], temb)
+        if c.addition_embed_type == "text_time":
+            self.add_time_proj = Timesteps(c.addition_time_embed_dim)
+            self.add_embedding = TimestepEmbedding(c.projection_class_embeddings_input_dim, temb)
+        self.down_blocks = nn.ModuleList([])
+        self.up_blocks = nn.ModuleList([])
+        heads, tl = c.attention_head_dim, c.transformer_layers_per_block
+        g, eps, lin = c.norm_num_groups, c.norm_eps, c.use_linear_projection
+        out_ch = boc[0]
+        for i, t in enumerate(c.down_block_types):
+            in_ch, out_ch = out_ch, boc[i]
+            final = i == len(boc) - 1
+            if t == "DownBlock2D":
+                self.down_blocks.append(DownBlock2D(in_ch, out_ch, temb, c.layers_per_block, g, eps, not final))
+            elif t == "CrossAttnDownBlock2D":
+                self.down_blocks.append(CrossAttnDownBlock2D(in_ch, out_ch, temb, c.layers_per_block, tl[i], heads[i],
+                                                             c.cross_attention_dim, g, eps, not final, lin))
+            else:
+                raise ValueError(f"unsupported down block {t}")
+        self.mid_block = UNetMidBlock2DCrossAttn(boc[-1], temb, tl[-1], heads[-1], c.cross_attention_dim, g, eps, lin)
+        rboc, rheads, rtl = list(reversed(boc)), list(reversed(heads)), list(reversed(tl))
+        out_ch = rboc[0]
+        for i, t in enumerate(c.up_block_types):
+            final = i == len(boc) - 1
+            prev, out_ch = out_ch, rboc[i]
+            in_ch = rboc[min(i + 1, len(boc) - 1)]
+            if t == "UpBlock2D":
+                self.up_blocks.append(UpBlock2D(in_ch, prev, out_ch, temb, c.layers_per_block + 1, g, eps, not final))
+            elif t == "CrossAttnUpBlock2D":
+                self.up_blocks.append(CrossAttnUpBlock2D(in_ch, prev, out_ch, temb, c.layers_per_block + 1, rtl[i],
+                                                         rheads[i], c.cross_attention_dim, g, eps, not final, lin))
+            else:
+                raise ValueError(f"unsupported up block {t}")
+        self.conv_norm_out = nn.GroupNorm(g, boc[0], eps=eps)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(boc[0], c.out_channels, 3, padding=1)
+        # engine state (not part of the state dict)
+        self._packed: Dict[int, torch.Tensor] = {}
+        self._lora_packs: Dict[tuple, _LoraPack] = {}
+        self._graphs: Dict[tuple, "_CapturedForward"] = {}
+        self._slider_scale_dev: Optional[torch.Tensor] = None
+        self.use_cuda_graph = False
+
+    # ---- diffusers-API shims used by the reference trainers (train_lora_xl.py:78-82) ----------------
+    def enable_xformers_memory_efficient_attention(self, *a, **k):
+        return None  # attention always runs in the flash kernel
+
+    @property
+    def dtype(self):
+        return self.conv_in.weight.dtype
+
+    @property
+    def device(self):
+        return self.conv_in.weight.device
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.__dict__.pop("_adapted_cache", None)
+        self.__dict__.pop("_leaf_by_id", None)
+        self._packed.clear()
+        self._lora_packs.clear()
+        self._graphs.clear()
+        self._slider_scale_dev = None
+        return out
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._packed.clear()
+        self._graphs.clear()
+        return out
+
+    # ---- frozen-weight packing -----------------------------------------------------------------------
+    def _w(self, leaf: nn.Module) -> torch.Tensor:
+        """Kernel-layout weight of a leaf (cached): Linear [N,K]; Conv 1x1 [N,K]; Conv 3x3 [Cout,3,3,Cin]."""
+        key = id(leaf)
+        w = self._packed.get(key)
+        if w is None:
+            p = leaf.weight.detach()
+            if p.dim() == 4:
+                p = p.permute(0, 2, 3, 1)
+                if p.shape[1] == 1:
+                    p = p.reshape(p.shape[0], -1)
+            w = p.to(BF16).contiguous()
+            self._packed[key] = w
+        return w
+
+    def _b(self, leaf: nn.Module) -> Optional[torch.Tensor]:
+        if leaf.bias is None:
+            return None
+        key = ("b", id(leaf))
+        b = self._packed.get(key)
+        if b is None:
+            b = leaf.bias.detach().to(BF16).contiguous()
+            self._packed[key] = b
+        return b
+
+    def _fused_w(self, leaves: List[nn.Module]) -> torch.Tensor:
+        key = ("fused",) + tuple(id(l) for l in leaves)
+        w = self._packed.get(key)
+        if w is None:
+            w = torch.cat([l.weight.detach().to(BF16) for l in leaves], dim=0).contiguous()
+            self._packed[key] = w
+        return w
+
+    # ---- LoRA packing --------------------------------------------------------------------------------
+    def _lora(self, leaves: List[nn.Module]) -> Optional[Lora]:
+        """sb200_lora for one fused call over `leaves` (all sharing the same input), or None when no leaf is
+        adapted or every multiplier is 0 (lora.py:256-258: outside `with network:` the delta is exactly 0)."""
+        adaptors = [_adaptor_of(l) for l in leaves]
+        if all(a is None for a in adaptors):
+            return None
+        scales = [float(a.multiplier) * float(a.scale) if a is not None else 0.0 for a in adaptors]
+        if all(s == 0.0 for s in scales):
+            return None
+        r = max(int(a.lora_dim) for a in adaptors if a is not None)
+        if r not in (4, 8):
+            raise NotImplementedError(f"LoRA rank {r}: the fused epilogue supports ranks 4 and 8")
+        rt = 16 if len(leaves) * r <= 16 else 32
+        if len(leaves) * r > 32:
+            raise NotImplementedError("too many adapted leaves fused into one call")
+        nz = [s for s in scales if s != 0.0]
+        common = nz[0] if all(abs(s - nz[0]) < 1e-12 for s in nz) else None
+        key_leaves = tuple(id(l) for l in leaves)
+        pack = self._lora_packs.setdefault(key_leaves, _LoraPack())
+        ver = tuple((a.lora_down.weight.data_ptr(), a.lora_down.weight._version, a.lora_up.weight.data_ptr(),
+                     a.lora_up.weight._version) if a is not None else None for a in adaptors)
+        ver = (ver, None if common is not None else tuple(scales))
+        group_n = leaves[0].weight.shape[0]
+        if pack.key != ver:
+            dev = leaves[0].weight.device
+            K = leaves[0].weight[0].numel()
+            N = sum(l.weight.shape[0] for l in leaves)
+            if pack.down is None:
+                pack.down = torch.zeros((rt, K), device=dev, dtype=BF16)
+                pack.up = torch.zeros((N, r), device=dev, dtype=BF16)
+            else:
+                pack.down.zero_()
+                pack.up.zero_()
+            n0 = 0
+            for gi, (leaf, a) in enumerate(zip(leaves, adaptors)):
+                n1 = n0 + leaf.weight.shape[0]
+                if a is not None:
+                    d = a.lora_down.weight.detach()
+                    if d.dim() == 4:
+                        d = d.permute(0, 2, 3, 1)
+                    rr = d.shape[0]
+                    pack.down[gi * r: gi * r + rr].copy_(d.reshape(rr, -1))
+                    u = a.lora_up.weight.detach().reshape(leaf.weight.shape[0], -1)
+                    if common is None:
+                        u = u.float() * scales[gi]
+                    pack.up[n0:n1, :rr].copy_(u)
+                n0 = n1
+            pack.key = ver
+        if self._slider_scale_dev is None:
+            self._slider_scale_dev = torch.ones(1, device=leaves[0].weight.device, dtype=torch.float32)
+        if self._capturing and common is not None:
+            # graph mode: the common scale is read from device memory at replay time
+            return Lora(pack.down, pack.up, r, group_n, 1.0, self._slider_scale_dev)
+        return Lora(pack.down, pack.up, r, group_n, common if common is not None else 1.0)
+
+    _capturing = False
+
+    # ---- forward pieces ------------------------------------------------------------------------------
+    def _resnet(self, blk: ResnetBlock2D, x0, x1, emb_act_in) -> torch.Tensor:
+        """x0 (and optional skip x1): [B,H,W,C*] NHWC.  emb: [B, 1280] (SiLU applied inside small_linear)."""
+        B, H, W, _ = x0.shape
+        n1 = blk.norm1
+        h = ops.groupnorm(x0, self._w_norm(n1)[0], self._w_norm(n1)[1], n1.num_groups, n1.eps, True, x1=x1)
+        temb = ops.small_linear(emb_act_in, self._w(blk.time_emb_proj), self._b(blk.time_emb_proj), act_in=True,
+                                lora=self._lora([blk.time_emb_proj]))
+        h = ops.conv3x3(h, self._w(blk.conv1), bias=self._b(blk.conv1), rowbias=temb, lora=self._lora([blk.conv1]))
+        n2 = blk.norm2
+        h = ops.groupnorm(h, self._w_norm(n2)[0], self._w_norm(n2)[1], n2.num_groups, n2.eps, True)
+        if blk.conv_shortcut is not None:
+            sc = blk.conv_shortcut
+            cout = sc.weight.shape[0]
+            res = ops.gemm(x0.view(-1, x0.shape[-1]), self._w(sc), bias=self._b(sc),
+                           x1=x1.view(-1, x1.shape[-1]) if x1 is not None else None,
+                           lora=self._lora([sc])).view(B, H, W, cout)
+        else:
+            assert x1 is None
+            res = x0
+        return ops.conv3x3(h, self._w(blk.conv2), bias=self._b(blk.conv2), resid=res, lora=self._lora([blk.conv2]))
+
+    def _w_norm(self, norm: nn.Module):
+        key = ("n", id(norm))
+        v = self._packed.get(key)
+        if v is None:
+            v = (norm.weight.detach().to(BF16).contiguous(), norm.bias.detach().to(BF16).contiguous())
+            self._packed[key] = v
+        return v
+
+    def _attn(self, attn: Attention, x_norm, resid, B, S, ctx=None, Sctx=0):
+        """x_norm: [B*S, C] normalised input; returns resid + to_out(attention)."""
+        C_ = attn.to_q.weight.shape[0]
+        if attn.dim_head != 64:
+            raise NotImplementedError(f"attention head dim {attn.dim_head}: the flash kernel is built for 64 "
+                                      "(SDXL); SD1.x head dims 40/80/160 are a later row of SURVEY.md §8f")
+        scale = attn.dim_head ** -0.5
+        if ctx is None:
+            leaves = [attn.to_q, attn.to_k, attn.to_v]
+            qkv = ops.gemm(x_norm, self._fused_w(leaves), lora=self._lora(leaves))
+            o = ops.attention(qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:], B, attn.heads, S, S, scale)
+        else:
+            q = ops.gemm(x_norm, self._w(attn.to_q), lora=self._lora([attn.to_q]))
+            kvl = [attn.to_k, attn.to_v]
+            kv = ops.gemm(ctx, self._fused_w(kvl), lora=self._lora(kvl))
+            o = ops.attention(q, kv[:, :C_], kv[:, C_:], B, attn.heads, S, Sctx, scale)
+        out = attn.to_out[0]
+        return ops.gemm(o, self._w(out), bias=self._b(out), resid=resid, lora=self._lora([out]))
+
+    def _transformer(self, tr: Transformer2DModel, x, ctx, Sctx) -> torch.Tensor:
+        B, H, W, C_ = x.shape
+        S = H * W
+        res = x.view(B * S, C_)
+        gn = tr.norm
+        h = ops.groupnorm(x, self._w_norm(gn)[0], self._w_norm(gn)[1], gn.num_groups, gn.eps, False).view(B * S, C_)
+        h = ops.gemm(h, self._w(tr.proj_in), bias=self._b(tr.proj_in))
+        for blk in tr.transformer_blocks:
+            n = ops.layernorm(h, *self._w_norm(blk.norm1), eps=blk.norm1.eps)
+            h = self._attn(blk.attn1, n, h, B, S)
+            n = ops.layernorm(h, *self._w_norm(blk.norm2), eps=blk.norm2.eps)
+            h = self._attn(blk.attn2, n, h, B, S, ctx=ctx, Sctx=Sctx)
+            n = ops.layernorm(h, *self._w_norm(blk.norm3), eps=blk.norm3.eps)
+            ffp, ffo = blk.ff.net[0].proj, blk.ff.net[2]
+            f = ops.gemm(n, self._w(ffp), bias=self._b(ffp), geglu=True)
+            h = ops.gemm(f, self._w(ffo), bias=self._b(ffo), resid=h)
+        h = ops.gemm(h, self._w(tr.proj_out), bias=self._b(tr.proj_out), resid=res)
+        return h.view(B, H, W, C_)
+
+    def _embeddings(self, timesteps_f32, B, added_cond_kwargs):
+        """Returns emb [B, temb] (pre-SiLU; every resnet applies SiLU in its time_emb_proj load)."""
+        te = self.time_embedding
+        t_emb = ops.sinusoid(timesteps_f32, self.time_proj.num_channels)
+        h = ops.small_linear(t_emb, self._w(te.linear_1), self._b(te.linear_1), act_out=True)
+        emb = ops.small_linear(h, self._w(te.linear_2), self._b(te.linear_2))
+        if getattr(self.config, "addition_embed_type", None) == "text_time":
+            if added_cond_kwargs is None or "text_embeds" not in added_cond_kwargs or "time_ids" not in added_cond_kwargs:
+                raise ValueError("addition_embed_type 'text_time' needs added_cond_kwargs['text_embeds','time_ids']")
+            text_embeds = added_cond_kwargs["text_embeds"].to(device=emb.device, dtype=BF16)
+            time_ids = added_cond_kwargs["time_ids"].to(device=emb.device, dtype=torch.float32)
+            tid = ops.sinusoid(time_ids.reshape(-1).contiguous(), self.add_time_proj.num_channels)
+            add = torch.cat([text_embeds, tid.view(B, -1)], dim=-1).contiguous()
+            ae = self.add_embedding
+            a = ops.small_linear(add, self._w(ae.linear_1), self._b(ae.linear_1), act_out=True)
+            emb = ops.small_linear(a, self._w(ae.linear_2), self._b(ae.linear_2), resid=emb)
+        return emb
+
+    def _forward_impl(self, sample, timesteps_f32, ehs, added_cond_kwargs, out_dtype):
+        B = sample.shape[0]
+        Sctx = ehs.shape[1]
+        ctx = ehs.reshape(B * Sctx, ehs.shape[-1])
+        emb = self._embeddings(timesteps_f32, B, added_cond_kwargs)
+        h = ops.conv_in(sample, self._w(self.conv_in), self._b(self.conv_in))
+        skips = [h]
+        for blk in self.down_blocks:
+            attns = getattr(blk, "attentions", None)
+            for i, rn in enumerate(blk.resnets):
+                h = self._resnet(rn, h, None, emb)
+                if attns is not None:
+                    h = self._transformer(attns[i], h, ctx, Sctx)
+                skips.append(h)
+            if blk.downsamplers is not None:
+                conv = blk.downsamplers[0].conv
+                h = ops.conv3x3(h, self._w(conv), stride=2, bias=self._b(conv), lora=self._lora([conv]))
+                skips.append(h)
+        mid = self.mid_block
+        h = self._resnet(mid.resnets[0], h, None, emb)
+        h = self._transformer(mid.attentions[0], h, ctx, Sctx)
+        h = self._resnet(mid.resnets[1], h, None, emb)
+        for blk in self.up_blocks:
+            attns = getattr(blk, "attentions", None)
+            for i, rn in enumerate(blk.resnets):
+                h = self._resnet(rn, h, skips.pop(), emb)
+                if attns is not None:
+                    h = self._transformer(attns[i], h, ctx, Sctx)
+            if blk.upsamplers is not None:
+                conv = blk.upsamplers[0].conv
+                h = ops.upsample2x(h)
+                h = ops.conv3x3(h, self._w(conv), bias=self._b(conv), lora=self._lora([conv]))
+        gn = self.conv_norm_out
+        h = ops.groupnorm(h, self._w_norm(gn)[0], self._w_norm(gn)[1], gn.num_groups, gn.eps, True)
+        return ops.conv_out(h, self._w(self.conv_out), self._b(self.conv_out), out_dtype=out_dtype)
+
+    # ---- public forward --------------------------------------------------------------------------------
+    def forward(self, sample, timestep, encoder_hidden_states=None, added_cond_kwargs=None,
+                cross_attention_kwargs=None, return_dict: bool = True, **unused):
+        self._check_no_grad_needed()
+        with torch.no_grad():
+            return self._forward_nograd(sample, timestep, encoder_hidden_states, added_cond_kwargs, return_dict)
+
+    def _forward_nograd(self, sample, timestep, encoder_hidden_states, added_cond_kwargs, return_dict):
+        if not sample.is_cuda:
+            raise RuntimeError("sliders_b200.UNet2DConditionModel runs only on a CUDA (sm_100) device; "
+                               "there is no CPU path (the CPU oracle lives under oracle/ for tests)")
+        B = sample.shape[0]
+        dev = sample.device
+        if torch.is_tensor(timestep):
+            t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+            if t.numel() == 1:
+                t = t.expand(B)
+        else:
+            t = torch.full((B,), float(timestep), device=dev, dtype=torch.float32)
+        t = t.contiguous()
+        out_dtype = sample.dtype if sample.dtype in (torch.float32, BF16) else BF16
+        x = sample if sample.dtype in (torch.float32, BF16) else sample.to(BF16)
+        x = x.contiguous()
+        ehs = encoder_hidden_states.to(device=dev, dtype=BF16).contiguous()
+        if self.use_cuda_graph:
+            out = self._graphed(x, t, ehs, added_cond_kwargs, out_dtype)
+        else:
+            out = self._forward_impl(x, t, ehs, added_cond_kwargs, out_dtype)
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(sample=out)
+
+    # ---- CUDA-graph replay -----------------------------------------------------------------------------
+    def _adapted_leaves(self):
+        cache = self.__dict__.get("_adapted_cache")
+        if cache is None:
+            cache = [m for m in self.modules() if isinstance(m, (nn.Linear, nn.Conv2d))]
+            self.__dict__["_adapted_cache"] = cache
+        return [(m, a) for m in cache for a in (_adaptor_of(m),) if a is not None]
+
+    def _lora_signature(self):
+        """(signature, common slider factor).  Which adaptors contribute is baked into a captured graph; when
+        every active adaptor has the same multiplier*alpha/rank (the only thing `with network:` /
+        `set_lora_slider` can produce, lora.py:249-258) that factor is a device-side scalar and the
+        signature does not depend on it; otherwise the individual factors are part of the signature."""
+        scales = [float(a.multiplier) * float(a.scale) for _, a in self._adapted_leaves()]
+        nz = [s for s in scales if s != 0.0]
+        if not nz:
+            return (tuple(False for _ in scales), None), None
+        if all(abs(s - nz[0]) < 1e-12 for s in nz):
+            return (tuple(s != 0.0 for s in scales), None), nz[0]
+        return (tuple(s != 0.0 for s in scales), tuple(scales)), None
+
+    def _check_no_grad_needed(self):
+        if not torch.is_grad_enabled():
+            return
+        for _, a in self._adapted_leaves():
+            if float(a.multiplier) != 0.0 and a.lora_down.weight.requires_grad:
+                raise NotImplementedError(
+                    "sliders_b200 round 1 implements the forward (denoise / inference) path only; the "
+                    "backward-to-LoRA kernels are SURVEY.md §8(f) rank 1.  Call under torch.no_grad().")
+
+    def _graphed(self, x, t, ehs, added, out_dtype):
+        sig, _ = self._lora_signature()
+        addk = None
+        if added is not None:
+            addk = (tuple(added["text_embeds"].shape), tuple(added["time_ids"].shape))
+        key = (tuple(x.shape), x.dtype, tuple(ehs.shape), addk, out_dtype, sig)
+        cap = self._graphs.get(key)
+        if cap is None:
+            cap = _CapturedForward(self, x, t, ehs, added, out_dtype)
+            self._graphs[key] = cap
+        return cap.replay(self, x, t, ehs, added)
+
+
+class _CapturedForward:
+    """One captured CUDA graph of the whole UNet forward for fixed shapes (inputs are copied into static
+    buffers; the LoRA slider factor and the timestep are device-side values, so one graph serves every
+    denoise step and every slider scale)."""
+
+    def __init__(self, unet: UNet2DConditionModel, x, t, ehs, added, out_dtype):
+        self.x, self.t, self.ehs = x.clone(), t.clone(), ehs.clone()
+        self.added = None
+        if added is not None:
+            self.added = {"text_embeds": added["text_embeds"].to(device=x.device, dtype=BF16).clone(),
+                          "time_ids": added["time_ids"].to(device=x.device, dtype=torch.float32).clone()}
+        # per-adaptor effective scale folded into one device scalar: graphs assume a common scale
+        stream = torch.cuda.Stream(device=x.device)
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            for _ in range(2):  # warm-up: fills weight / LoRA packing caches and the TMA descriptor cache
+                unet._forward_impl(self.x, self.t, self.ehs, self.added, out_dtype)
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        unet._capturing = True
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = unet._forward_impl(self.x, self.t, self.ehs, self.added, out_dtype)
+        finally:
+            unet._capturing = False
+        self.launches = None
+
+    def replay(self, unet: UNet2DConditionModel, x, t, ehs, added):
+        self.x.copy_(x)
+        self.t.copy_(t)
+        self.ehs.copy_(ehs)
+        if added is not None:
+            self.added["text_embeds"].copy_(added["text_embeds"])
+            self.added["time_ids"].copy_(added["time_ids"])
+        _, common = unet._lora_signature()
+        if unet._slider_scale_dev is not None:
+            unet._slider_scale_dev.fill_(1.0 if common is None else common)
+        # refresh packed LoRA weights if the optimiser changed them (same storage, so the graph sees them)
+        unet._refresh_lora_packs()
+        self.graph.replay()
+        return self.out.clone()
+
+
+def _refresh(self: UNet2DConditionModel):
+    leaves_by_id = getattr(self, "_leaf_by_id", None)
+    if leaves_by_id is None:
+        leaves_by_id = {id(m): m for m in self.modules() if isinstance(m, (nn.Linear, nn.Conv2d))}
+        self._leaf_by_id = leaves_by_id
+    for key in list(self._lora_packs.keys()):
+        leaves = [leaves_by_id[i] for i in key]
+        self._lora(leaves)
+
+
+UNet2DConditionModel._refresh_lora_packs = _refresh
