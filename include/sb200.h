@@ -99,7 +99,10 @@ int sb200_attention(void* handle, void* stream, const void* q, int ldq, const vo
                     float scale);
 
 /* GroupNorm (+ optional SiLU) over an NHWC tensor that may be the channel concat of two sources.
- * Replaces torch GroupNorm + SiLU in ResnetBlock2D / Transformer2DModel / conv_norm_out. */
+ * Replaces torch GroupNorm + SiLU in ResnetBlock2D / Transformer2DModel / conv_norm_out.
+ * stats_ws: caller-owned fp32 scratch of at least SB200_GN_WS_FLOATS(B, groups) floats. The reduction is
+ * atomic-free, so results are bit-reproducible run to run. */
+#define SB200_GN_WS_FLOATS(B, groups) ((size_t)(B) * (groups) * 2 * (128 + 1))
 int sb200_groupnorm(void* handle, void* stream, const void* x0, int ldx0, int C0, const void* x1,
                     int ldx1, int C1, const void* gamma, const void* beta, void* out, int ldo, int B,
                     int HW, int groups, float eps, int silu, float* stats_ws);

@@ -9,7 +9,7 @@
 namespace sb200 {
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics: stats[b][g] = {sum, sumsq} over (HW x C/G) elements; the input may be the
+// GroupNorm statistics over (HW x C/G) elements per (batch, group); the input may be the
 // channel concat of two NHWC sources.
 // grid (chunks, B); block = (C/8) * rows_par threads: thread (r, cv) owns channel vector cv and walks
 // rows r, r + rows_par, ... of its chunk.
@@ -22,15 +22,17 @@ struct GnArgs {
   int rows_per_block;
 };
 
-__global__ void gn_stats_kernel(GnArgs a, float* __restrict__ stats) {
-  extern __shared__ float sh[];  // [2 * groups]
+constexpr int kGnMaxChunks = 128;
+
+// Deterministic (atomic-free) reduction: per-thread partials -> shared memory -> one thread per group sums
+// its channels in a fixed order -> partial[b][chunk][g] in global; gn_finalize_kernel sums the chunks in order.
+__global__ void gn_stats_kernel(GnArgs a, float* __restrict__ partial) {
+  extern __shared__ float sh[];  // [rows_par][C][2]
   const int nvec = a.C >> 3;
   const int cv = threadIdx.x % nvec;
   const int r0 = threadIdx.x / nvec;
   const int rows_par = blockDim.x / nvec;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   const int c = cv << 3;
   const __nv_bfloat16* src;
   int ld, cc;
@@ -44,29 +46,56 @@ __global__ void gn_stats_kernel(GnArgs a, float* __restrict__ stats) {
   float s[8], ss[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
-  if (r0 < rows_par) {
-    for (int r = row_begin + r0; r < row_end; r += rows_par) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(b) * a.HW + r) * ld + cc));
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  for (int r = row_begin + r0; r < row_end; r += rows_par) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(b) * a.HW + r) * ld + cc));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float lo = bf16_lo(w[i]), hi = bf16_hi(w[i]);
-        s[2 * i] += lo;
-        ss[2 * i] += lo * lo;
-        s[2 * i + 1] += hi;
-        ss[2 * i + 1] += hi * hi;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (c + i) / a.cpg;
-      atomicAdd(&sh[2 * g], s[i]);
-      atomicAdd(&sh[2 * g + 1], ss[i]);
+    for (int i = 0; i < 4; ++i) {
+      const float lo = bf16_lo(w[i]), hi = bf16_hi(w[i]);
+      s[2 * i] += lo;
+      ss[2 * i] += lo * lo;
+      s[2 * i + 1] += hi;
+      ss[2 * i + 1] += hi * hi;
     }
   }
+  float* mine = sh + (static_cast<size_t>(r0) * a.C + c) * 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mine[2 * i] = s[i];
+    mine[2 * i + 1] = ss[i];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x)
-    atomicAdd(&stats[static_cast<size_t>(b) * 2 * a.groups + i], sh[i]);
+  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+    float S = 0.f, SS = 0.f;
+    for (int r = 0; r < rows_par; ++r) {
+      const float* row = sh + (static_cast<size_t>(r) * a.C + g * a.cpg) * 2;
+      for (int ci = 0; ci < a.cpg; ++ci) {
+        S += row[2 * ci];
+        SS += row[2 * ci + 1];
+      }
+    }
+    float* out = partial + ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * a.groups + g) * 2;
+    out[0] = S;
+    out[1] = SS;
+  }
+}
+
+// final[b][g] = {mean, rstd}
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ final_stats,
+                                   int chunks, int groups, float inv_n, float eps) {
+  const int b = blockIdx.x;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float S = 0.f, SS = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      const float* pp = partial + ((static_cast<size_t>(b) * chunks + k) * groups + g) * 2;
+      S += pp[0];
+      SS += pp[1];
+    }
+    const float mean = S * inv_n;
+    const float var = fmaxf(SS * inv_n - mean * mean, 0.f);
+    final_stats[(static_cast<size_t>(b) * groups + g) * 2] = mean;
+    final_stats[(static_cast<size_t>(b) * groups + g) * 2 + 1] = rsqrtf(var + eps);
+  }
 }
 
 struct GnApplyArgs {
@@ -84,7 +113,6 @@ __global__ void gn_apply_kernel(GnApplyArgs a, const float* __restrict__ stats) 
   const GnArgs& in = a.in;
   const int nvec = in.C >> 3;
   const size_t total = static_cast<size_t>(a.B) * in.HW * nvec;
-  const float inv_n = 1.f / (static_cast<float>(in.HW) * in.cpg);
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(idx % nvec);
@@ -118,9 +146,8 @@ __global__ void gn_apply_kernel(GnApplyArgs a, const float* __restrict__ stats) 
       const int g = (c + i) / in.cpg;
       if (g != g_prev) {
         g_prev = g;
-        mean = st[2 * g] * inv_n;
-        const float var = fmaxf(st[2 * g + 1] * inv_n - mean * mean, 0.f);
-        rstd = rsqrtf(var + a.eps);
+        mean = st[2 * g];
+        rstd = st[2 * g + 1];
       }
       const float gm = (i & 1) ? bf16_hi(gw[i >> 1]) : bf16_lo(gw[i >> 1]);
       const float bt = (i & 1) ? bf16_hi(bw[i >> 1]) : bf16_lo(bw[i >> 1]);
@@ -240,13 +267,18 @@ extern "C" int sb200_groupnorm(void* handle, void* stream, const void* x0, int l
   const int threads = nvec * rows_par;
   // enough blocks to fill the machine, but each block should walk >= 8 rows per thread
   int chunks = (ctx->num_sms * 4 + B - 1) / B;
+  if (chunks > kGnMaxChunks) chunks = kGnMaxChunks;
   int rows_per_block = (HW + chunks - 1) / chunks;
   const int min_rows = rows_par * 8;
   if (rows_per_block < min_rows) rows_per_block = min_rows;
   chunks = (HW + rows_per_block - 1) / rows_per_block;
   a.rows_per_block = rows_per_block;
-  SB200_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * B, s));
-  gn_stats_kernel<<<dim3(chunks, B), threads, sizeof(float) * 2 * groups, s>>>(a, stats_ws);
+  // workspace: partial[B][chunks][G][2] followed by final[B][G][2]
+  float* final_stats = stats_ws + static_cast<size_t>(B) * kGnMaxChunks * groups * 2;
+  gn_stats_kernel<<<dim3(chunks, B), threads, sizeof(float) * 2 * C * rows_par, s>>>(a, stats_ws);
+  SB200_CUDA_CHECK(cudaGetLastError());
+  gn_finalize_kernel<<<B, 64, 0, s>>>(stats_ws, final_stats, chunks, groups,
+                                      1.f / (static_cast<float>(HW) * a.cpg), eps);
   SB200_CUDA_CHECK(cudaGetLastError());
   GnApplyArgs ap;
   ap.in = a;
@@ -261,7 +293,7 @@ extern "C" int sb200_groupnorm(void* handle, void* stream, const void* x0, int l
   int blocks = static_cast<int>((total + 255) / 256);
   const int max_blocks = ctx->num_sms * 16;
   if (blocks > max_blocks) blocks = max_blocks;
-  gn_apply_kernel<<<blocks, 256, 0, s>>>(ap, stats_ws);
+  gn_apply_kernel<<<blocks, 256, 0, s>>>(ap, final_stats);
   SB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

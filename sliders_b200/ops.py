@@ -16,7 +16,7 @@ BF16 = torch.bfloat16
 
 # launches issued through this module since import (bench.py reports it as gpu_launches)
 launch_count = 0
-_KERNELS_PER_CALL = {"groupnorm": 3}  # memset + stats + apply
+_KERNELS_PER_CALL = {"groupnorm": 3}  # stats + finalize + apply
 
 
 def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -33,9 +33,28 @@ def _ctx(t: torch.Tensor):
     return _cabi.handle(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
-def _count(name: str = "") -> None:
-    global launch_count
+# Optional per-call device timing (bench.py's roofline leg): when `profile_log` is a list every wrapper brackets
+# its launch with CUDA events on the launching stream and appends (name, flops, start_event, end_event).
+profile_log = None
+_pending_start = None
+
+
+def _begin():
+    global _pending_start
+    if profile_log is not None:
+        _pending_start = torch.cuda.Event(enable_timing=True)
+        _pending_start.record()
+    return _cabi.load()
+
+
+def _count(name: str = "", flops: float = 0.0) -> None:
+    global launch_count, _pending_start
     launch_count += _KERNELS_PER_CALL.get(name, 1)
+    if profile_log is not None and _pending_start is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        profile_log.append((name or "other", flops, _pending_start, end))
+        _pending_start = None
 
 
 class Lora:
@@ -74,12 +93,12 @@ def gemm(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowbias=None, rows_per_
     nout = N // 2 if geglu else N
     if out is None:
         out = torch.empty((M, nout), device=x.device, dtype=BF16)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_gemm(
         _ctx(x), _stream(), _p(x), x.stride(0), _p(x1), x1.stride(0) if x1 is not None else 0, K0,
         _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, flags, _p(bias), _p(rowbias), rows_per_batch,
         _p(resid), resid.stride(0) if resid is not None else 0, lora.ref() if lora is not None else None, bn))
-    _count()
+    _count("gemm", 2.0 * M * N * K)
     return out
 
 
@@ -99,12 +118,12 @@ def conv3x3(x0: torch.Tensor, w_packed: torch.Tensor, *, x1: Optional[torch.Tens
     if lora is not None:
         flags |= EPI_LORA
     out = torch.empty((B, H // stride, W // stride, Cout), device=x0.device, dtype=BF16)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_conv3x3(
         _ctx(x0), _stream(), _p(x0), x0.stride(2), _p(x1), x1.stride(2) if x1 is not None else 0, C0, C1,
         _p(w_packed), _p(out), Cout, B, H, W, Cout, stride, flags, _p(bias), _p(rowbias), _p(resid),
         resid.stride(2) if resid is not None else 0, lora.ref() if lora is not None else None, bn))
-    _count()
+    _count("conv3x3", 2.0 * B * (H // stride) * (W // stride) * Cout * 9 * (C0 + C1))
     return out
 
 
@@ -112,10 +131,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: 
               scale: float) -> torch.Tensor:
     """q/k/v: 2-D (possibly column-sliced) token matrices, head dim 64.  One `attention_kernel`."""
     out = torch.empty((B * Sq, heads * 64), device=q.device, dtype=BF16)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_attention(_ctx(q), _stream(), _p(q), q.stride(0), _p(k), k.stride(0), _p(v),
                                     v.stride(0), _p(out), out.stride(0), B, heads, Sq, Skv, float(scale)))
-    _count()
+    _count("attention", 4.0 * B * heads * Sq * Skv * 64)
     return out
 
 
@@ -128,8 +147,8 @@ def groupnorm(x0: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool
     C1 = x1.shape[-1] if x1 is not None else 0
     out = torch.empty(shp[:-1] + (C0 + C1,), device=x0.device, dtype=BF16)
     if stats_ws is None:
-        stats_ws = torch.empty(B * groups * 2, device=x0.device, dtype=torch.float32)
-    lib = _cabi.load()
+        stats_ws = torch.empty(B * groups * 2 * 129, device=x0.device, dtype=torch.float32)  # SB200_GN_WS_FLOATS
+    lib = _begin()
     _cabi.check(lib.sb200_groupnorm(_ctx(x0), _stream(), _p(x0), x0.stride(-2), C0, _p(x1),
                                     x1.stride(-2) if x1 is not None else 0, C1, _p(gamma), _p(beta), _p(out),
                                     C0 + C1, B, HW, groups, float(eps), int(silu), _p(stats_ws)))
@@ -140,7 +159,7 @@ def groupnorm(x0: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool
 def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
     M, Cc = x.shape
     out = torch.empty((M, Cc), device=x.device, dtype=BF16)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_layernorm(_ctx(x), _stream(), _p(x), x.stride(0), _p(gamma), _p(beta), _p(out), Cc, M,
                                     Cc, float(eps)))
     _count()
@@ -152,7 +171,7 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias=None, *, act_in: bool = 
     M, K = x.shape
     N = w.shape[0]
     out = torch.empty((M, N), device=x.device, dtype=BF16)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_small_linear(_ctx(x), _stream(), _p(x), x.stride(0), _p(w), w.stride(0), _p(bias),
                                        _p(out), N, M, N, K, int(act_in), int(act_out),
                                        lora.ref() if lora is not None else None, _p(resid)))
@@ -164,7 +183,7 @@ def sinusoid(values: torch.Tensor, dim: int) -> torch.Tensor:
     """values: fp32 [n] on device -> [n, dim] bf16 ([cos | sin])."""
     n = values.numel()
     out = torch.empty((n, dim), device=values.device, dtype=BF16)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_sinusoid(_ctx(values), _stream(), _p(values), n, dim, _p(out), dim))
     _count()
     return out
@@ -176,7 +195,7 @@ def conv_in(latent: torch.Tensor, w_packed: torch.Tensor, bias) -> torch.Tensor:
     assert Cc == 4 and latent.is_contiguous()
     Cout = w_packed.shape[0]
     out = torch.empty((B, H, W, Cout), device=latent.device, dtype=BF16)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_conv_in(_ctx(latent), _stream(), _p(latent), int(latent.dtype == torch.float32),
                                   _p(w_packed), _p(bias), _p(out), B, H, W, Cout))
     _count()
@@ -186,7 +205,7 @@ def conv_in(latent: torch.Tensor, w_packed: torch.Tensor, bias) -> torch.Tensor:
 def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias, out_dtype=BF16) -> torch.Tensor:
     B, H, W, Cin = x.shape
     out = torch.empty((B, 4, H, W), device=x.device, dtype=out_dtype)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_conv_out(_ctx(x), _stream(), _p(x), _p(w_packed), _p(bias), _p(out),
                                    int(out_dtype == torch.float32), B, H, W, Cin))
     _count()
@@ -196,23 +215,31 @@ def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias, out_dtype=BF16) -> t
 def upsample2x(x: torch.Tensor) -> torch.Tensor:
     B, H, W, Cc = x.shape
     out = torch.empty((B, 2 * H, 2 * W, Cc), device=x.device, dtype=BF16)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_upsample2x(_ctx(x), _stream(), _p(x), _p(out), B, H, W, Cc))
     _count()
     return out
 
 
 def cfg_ddim(eps2: torch.Tensor, guidance: float, x: Optional[torch.Tensor] = None, a_t: float = 1.0,
-             a_prev: float = 1.0, out_dtype=None):
-    """eps2 = [uncond batch ; cond batch] (contiguous).  Returns (guided_eps, x_prev or None)."""
-    n = eps2.numel() // 2
+             a_prev: float = 1.0, out_dtype=None, single: bool = False):
+    """eps2 = [uncond batch ; cond batch] (contiguous).  Returns (guided_eps, x_prev or None).
+    single=True: eps2 is one already-guided eps batch and guidance must be 0 (plain DDIM step)."""
+    if single:
+        assert guidance == 0.0
+        n = eps2.numel()
+        shape = tuple(eps2.shape)
+    else:
+        n = eps2.numel() // 2
+        shape = (eps2.shape[0] // 2,) + tuple(eps2.shape[1:])
+    if eps2.dtype not in (torch.float32, BF16):
+        eps2 = eps2.to(torch.float32)
     out_dtype = out_dtype or (x.dtype if x is not None else eps2.dtype)
-    shape = (eps2.shape[0] // 2,) + tuple(eps2.shape[1:])
     eps_out = torch.empty(shape, device=eps2.device, dtype=out_dtype)
     x_prev = torch.empty(shape, device=eps2.device, dtype=out_dtype) if x is not None else None
     if x is not None and x.dtype != out_dtype:
         x = x.to(out_dtype)
-    lib = _cabi.load()
+    lib = _begin()
     _cabi.check(lib.sb200_cfg_ddim(_ctx(eps2), _stream(), _p(eps2), int(eps2.dtype == torch.float32),
                                    float(guidance), _p(x), float(a_t), float(a_prev), _p(x_prev), _p(eps_out),
                                    int(out_dtype == torch.float32), n))

@@ -1,0 +1,79 @@
+"""Multi-GPU fan-out of conditioned eps-predictions: one process per GPU (torchrun),
+`torch.distributed` for the plumbing (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+
+The reference is single-process (`--device N`, train_lora_xl.py:414).  What shards naturally is the batch of
+*independent* conditioned passes: the 4 predictions x CFG halves of a text-slider iteration
+(train_lora_xl.py:236-322), the (high, low) x CFG passes of an image-slider iteration
+(train_lora-scale-xl.py:312-372), or the prompts x scales of the inference sweep
+(generate_images_xl.py:495-508).  Weights and LoRA parameters are replicated; each rank runs its slice of the
+passes through the same kernels and the eps tensors ([B,4,h,w], 128 KiB per sample at 1024 px) are
+all-gathered so every rank can evaluate the loss.  The only other exchange on the training path is one
+all-reduce(sum) of the flat LoRA-gradient buffer (8.64 MB at rank 4) — `allreduce_lora_grads`.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of n_items owned by `rank`; the first n_items % world ranks get one extra."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def fanout_predict(predict: Callable[..., torch.Tensor], batch_args: Sequence[torch.Tensor],
+                   group: Optional[dist.ProcessGroup] = None, **kwargs) -> torch.Tensor:
+    """Run `predict(*batch_args_slice, **kwargs)` on this rank's slice of the leading (pass) dimension and
+    all-gather the per-pass results, so that every rank returns the full [n_passes, ...] tensor in pass order —
+    identical to what one rank computing all passes returns (passes are independent)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return predict(*batch_args, **kwargs)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = batch_args[0].shape[0]
+    lo, hi = shard_range(n, rank, world)
+    local = predict(*[a[lo:hi] for a in batch_args], **kwargs) if hi > lo else None
+    counts = [shard_range(n, r, world) for r in range(world)]
+    max_cnt = max(h - l for l, h in counts)
+    # pad to a common size so a single all_gather suffices (counts differ by at most one)
+    if local is None:
+        probe_shape = None
+    else:
+        probe_shape = tuple(local.shape[1:])
+    shape_list: List[Optional[tuple]] = [None] * world
+    dist.all_gather_object(shape_list, (probe_shape, str(local.dtype) if local is not None else None), group=group)
+    tail, dtype_s = next(s for s in shape_list if s[0] is not None)
+    dtype = getattr(torch, dtype_s.split(".")[-1])
+    dev = batch_args[0].device
+    buf = torch.zeros((max_cnt,) + tuple(tail), device=dev, dtype=dtype)
+    if local is not None:
+        buf[: hi - lo].copy_(local)
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    return torch.cat([g[: h - l] for g, (l, h) in zip(gathered, counts)], dim=0)
+
+
+def allreduce_lora_grads(params: Sequence[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None) -> None:
+    """Sum LoRA gradients over ranks with ONE collective on a flat buffer (ranks that held no graph contribute
+    zeros), then scatter the result back into the .grad views."""
+    if not dist.is_available() or not dist.is_initialized():
+        return
+    ps = [p for p in params if p.requires_grad]
+    if not ps:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in ps:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n

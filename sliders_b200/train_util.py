@@ -1,0 +1,105 @@
+"""Host-side mirror of the reference's UNet call sites, trainscripts/textsliders/train_util.py — same
+function names, argument meaning and return values, so the trainers / parity tests read like the reference:
+
+  get_random_noise :20-33      get_initial_latents :43-57     concat_embeddings :136-141
+  predict_noise    :145-171    diffusion :175-196             predict_noise_xl :220-260
+  diffusion_xl     :263-294    get_add_time_ids :298-333
+
+`predict_noise(_xl)` keep the reference's dataflow (CFG pair batched along dim 0, guidance applied after the
+UNet); the UNet forward runs in sliders_b200 kernels and the CFG combine (+ DDIM update in `diffusion(_xl)`)
+in the fused `cfg_ddim_kernel`.  `rescale_noise_cfg` is computed-and-discarded in the reference (:256-260,
+SURVEY.md C.3) and is therefore not evaluated here.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+UNET_IN_CHANNELS = 4
+VAE_SCALE_FACTOR = 8
+UNET_ATTENTION_TIME_EMBED_DIM = 256
+TEXT_ENCODER_2_PROJECTION_DIM = 1280
+UNET_PROJECTION_CLASS_EMBEDDING_INPUT_DIM = 2816
+
+
+def get_random_noise(batch_size: int, height: int, width: int, generator: torch.Generator = None) -> torch.Tensor:
+    return torch.randn((batch_size, UNET_IN_CHANNELS, height // VAE_SCALE_FACTOR, width // VAE_SCALE_FACTOR),
+                       generator=generator, device="cpu")
+
+
+def get_initial_latents(scheduler, n_imgs: int, height: int, width: int, n_prompts: int, generator=None) -> torch.Tensor:
+    noise = get_random_noise(n_imgs, height, width, generator=generator).repeat(n_prompts, 1, 1, 1)
+    return noise * scheduler.init_noise_sigma
+
+
+def concat_embeddings(unconditional: torch.Tensor, conditional: torch.Tensor, n_imgs: int):
+    return torch.cat([unconditional, conditional]).repeat_interleave(n_imgs, dim=0)
+
+
+def _unet_pair(unet, latents, timestep, text_embeddings, added_cond_kwargs=None):
+    """The CFG-batched UNet call (train_util.py:154-163 / :232-247): returns eps for [uncond ; cond]."""
+    latent_model_input = torch.cat([latents] * 2)
+    kwargs = {"added_cond_kwargs": added_cond_kwargs} if added_cond_kwargs is not None else {}
+    return unet(latent_model_input, timestep, encoder_hidden_states=text_embeddings, **kwargs).sample
+
+
+def predict_noise(unet, scheduler, timestep, latents, text_embeddings, guidance_scale=7.5) -> torch.Tensor:
+    latents = scheduler.scale_model_input(latents, timestep)
+    noise_pred = _unet_pair(unet, latents, timestep, text_embeddings)
+    guided, _ = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, out_dtype=noise_pred.dtype)
+    return guided
+
+
+def predict_noise_xl(unet, scheduler, timestep, latents, text_embeddings, add_text_embeddings, add_time_ids,
+                     guidance_scale=7.5, guidance_rescale=0.7) -> torch.Tensor:
+    latents = scheduler.scale_model_input(latents, timestep)
+    added = {"text_embeds": add_text_embeddings, "time_ids": add_time_ids}
+    noise_pred = _unet_pair(unet, latents, timestep, text_embeddings, added)
+    guided, _ = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, out_dtype=noise_pred.dtype)
+    return guided
+
+
+def _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_scale, total_timesteps, start_timesteps):
+    for timestep in scheduler.timesteps[start_timesteps:total_timesteps]:
+        x = scheduler.scale_model_input(latents, timestep)
+        noise_pred = _unet_pair(unet, x, timestep, text_embeddings, added)
+        a_t, a_prev = scheduler._alphas_for(timestep)
+        # fused: eps = u + g (c - u);  x_{t-1} = DDIM(eps, x_t)
+        _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), a_t, a_prev,
+                                  out_dtype=latents.dtype)
+    return latents
+
+
+@torch.no_grad()
+def diffusion(unet, scheduler, latents, text_embeddings, total_timesteps: int = 1000, start_timesteps=0,
+              guidance_scale=7.5, **kwargs):
+    return _denoise_loop(unet, scheduler, latents, text_embeddings, None, guidance_scale, total_timesteps,
+                         start_timesteps)
+
+
+@torch.no_grad()
+def diffusion_xl(unet, scheduler, latents, text_embeddings, add_text_embeddings, add_time_ids,
+                 guidance_scale: float = 1.0, total_timesteps: int = 1000, start_timesteps=0):
+    added = {"text_embeds": add_text_embeddings, "time_ids": add_time_ids}
+    return _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_scale, total_timesteps,
+                         start_timesteps)
+
+
+def get_add_time_ids(height: int, width: int, dynamic_crops: bool = False, dtype: torch.dtype = torch.float32):
+    if dynamic_crops:
+        random_scale = torch.rand(1).item() * 2 + 1
+        original_size = (int(height * random_scale), int(width * random_scale))
+        crops_coords_top_left = (torch.randint(0, original_size[0] - height, (1,)).item(),
+                                 torch.randint(0, original_size[1] - width, (1,)).item())
+        target_size = (height, width)
+    else:
+        original_size, crops_coords_top_left, target_size = (height, width), (0, 0), (height, width)
+    add_time_ids = list(original_size + crops_coords_top_left + target_size)
+    passed = UNET_ATTENTION_TIME_EMBED_DIM * len(add_time_ids) + TEXT_ENCODER_2_PROJECTION_DIM
+    if passed != UNET_PROJECTION_CLASS_EMBEDDING_INPUT_DIM:
+        raise ValueError(f"Model expects an added time embedding vector of length "
+                         f"{UNET_PROJECTION_CLASS_EMBEDDING_INPUT_DIM}, but a vector of {passed} was created.")
+    return torch.tensor([add_time_ids], dtype=dtype)

@@ -93,7 +93,7 @@ def gn_case(B, HW, C0, C1, silu, eps=1e-5, seed=0):
     x0 = x[..., :C0].contiguous()
     x1 = x[..., C0:].contiguous() if C1 else None
     out = torch.full((B, HW, Cc), float("nan"), device=dev, dtype=BF)
-    ws = torch.empty(B * 64, device=dev, dtype=torch.float32)
+    ws = torch.empty(B * 32 * 2 * 129, device=dev, dtype=torch.float32)
     _cabi.check(lib.sb200_groupnorm(h, stream(), ptr(x0), C0, C0, ptr(x1), C1, C1, ptr(gamma), ptr(beta), ptr(out),
                                     Cc, B, HW, 32, eps, int(silu), ptr(ws)))
     torch.cuda.synchronize()
