@@ -52,7 +52,8 @@ int sb200_destroy(void* handle);
 /* LoRA side inputs of a fused GEMM / conv (reference: LoRAModule.forward, trainscripts/textsliders/lora.py:108-112).
  *   down : [rt, K] bf16, row j = lora_down.weight row (conv: [r, kh, kw, Cin] flattened tap-major); rows
  *          beyond the used ranks must be zero; rt is 16 or 32.
- *   up   : [N, r] bf16 (lora_up.weight); output column n uses down rows [(n / group_n) * r, +r), so one call
+ *   up   : [N, r] FP32 (lora_up.weight, widened once at pack time so the epilogue spends no cycles on
+ *          conversion); output column n uses down rows [(n / group_n) * r, +r), so one call
  *          can carry several adapted leaves that share an input (to_q|to_k|to_v fused: group_n = C).
  *   scale: multiplier * alpha / rank, a run-time scalar (the slider value changes per denoise step,
  *          eval-scripts/generate_images_xl.py:327-330).
@@ -73,7 +74,8 @@ typedef struct sb200_lora {
  * trainscripts/textsliders/train_util.py:242-247, with lora.py:108-112 folded in.
  * X may be split along K into two sources (skip-connection concat): columns [0, K0) come from x0 and
  * [K0, K) from x1 (x1 == NULL, K0 == K for a single source). K0 and K must be multiples of 64, N of 16.
- * bn is the N tile (0 = choose). */
+ * bn is the N tile (0 = choose by the cost model; | 0x1000 forces the CTA-pair (cta_group::2) kernel,
+ * | 0x2000 the single-CTA kernel — used by the tests). */
 int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, const void* x1, int ldx1, int K0,
                const void* w, int ldw, void* out, int ldo, int M, int N, int K, int flags,
                const void* bias, const void* rowbias, int rows_per_batch, const void* resid, int ldr,
@@ -112,8 +114,9 @@ int sb200_layernorm(void* handle, void* stream, const void* x, int ldx, const vo
                     const void* beta, void* out, int ldo, int M, int C, float eps);
 
 /* Small dense layers with M <= 64 rows (time / add embeddings, time_emb_proj):
- * out[M, N] = act_out( act_in(x)[M, K] . W[N, K]^T + bias (+ LoRA) ) + resid[M, N], act: 0 none, 1 SiLU;
- * resid (row stride N) may be NULL. */
+ * y = act_in(x)[M, K] . W[N, K]^T + bias (+ LoRA);  act_in: 0 none, 1 SiLU;  resid (row stride N) may be NULL;
+ *   act_out 0: out = y + resid      act_out 1: out = SiLU(y) + resid      act_out 2: out = SiLU(bf16(y + resid))
+ * (2 is how the summed time embedding reaches every ResnetBlock2D: emb is a bf16 tensor, then SiLU). */
 int sb200_small_linear(void* handle, void* stream, const void* x, int ldx, const void* w, int ldw,
                        const void* bias, void* out, int ldo, int M, int N, int K, int act_in,
                        int act_out, const sb200_lora* lora, const void* resid);

@@ -44,7 +44,7 @@ struct SmallLinearArgs {
   int M, N, K;
   int act_in, act_out;
   const __nv_bfloat16* down;  // [rt, K]
-  const __nv_bfloat16* up;    // [N, r]
+  const float* up;            // [N, r] fp32
   int r, group_n;
   float scale;
   const float* scale_dev;
@@ -126,11 +126,14 @@ __global__ void __launch_bounds__(kSlWarps * 32) small_linear_kernel(SmallLinear
             const int gj = (n / a.group_n - g_lo) * a.r;
             float l = 0.f;
             for (int j = 0; j < a.r; ++j)
-              l += t_sh[m0 + i][gj + j] * __bfloat162float(a.up[static_cast<size_t>(n) * a.r + j]);
+              l += t_sh[m0 + i][gj + j] * a.up[static_cast<size_t>(n) * a.r + j];
             y += (a.scale_dev ? a.scale * __ldg(a.scale_dev) : a.scale) * l;
           }
           if (a.act_out == 1) y = silu_f(y);
           if (a.resid) y += __bfloat162float(a.resid[static_cast<size_t>(m0 + i) * a.N + n]);
+          // act_out == 2: SiLU of the rounded sum (emb = t_emb + aug_emb is a bf16 tensor in the reference
+          // before ResnetBlock2D applies its nonlinearity)
+          if (a.act_out == 2) y = silu_f(__bfloat162float(__float2bfloat16(y)));
           a.out[static_cast<size_t>(m0 + i) * a.ldo + n] = __float2bfloat16(y);
         }
       }
@@ -145,8 +148,13 @@ template <typename TIn>
 __global__ void conv_in_kernel(const TIn* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                int B, int H, int W, int Cout) {
-  extern __shared__ __nv_bfloat16 wsh[];  // [Cout][36]
-  for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) wsh[i] = w[i];
+  // weights transposed to [36][Cout] so that a thread's 8 output channels of one tap element are a single
+  // 16-byte word and neighbouring threads (neighbouring channel octets) hit neighbouring banks
+  extern __shared__ __align__(16) __nv_bfloat16 wsh[];
+  for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) {
+    const int co = i / 36, k = i - co * 36;
+    wsh[k * Cout + co] = w[i];
+  }
   __syncthreads();
   const int ovec = Cout >> 3;
   const size_t total = static_cast<size_t>(B) * H * W * ovec;
@@ -176,13 +184,16 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, const __nv_bfloat16* _
       }
     float acc[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const int co = ov * 8 + o;
-      float s = bias ? __bfloat162float(bias[co]) : 0.f;
-      const __nv_bfloat16* wr = wsh + co * 36;
+    for (int o = 0; o < 8; ++o) acc[o] = bias ? __bfloat162float(bias[ov * 8 + o]) : 0.f;
 #pragma unroll
-      for (int k = 0; k < 36; ++k) s += patch[k] * __bfloat162float(wr[k]);
-      acc[o] = s;
+    for (int k = 0; k < 36; ++k) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(wsh + k * Cout + ov * 8);
+      const uint32_t ww4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        acc[2 * o] += patch[k] * bf16_lo(ww4[o]);
+        acc[2 * o + 1] += patch[k] * bf16_hi(ww4[o]);
+      }
     }
     uint4 o4;
     o4.x = pack_bf16x2(acc[0], acc[1]);
@@ -314,7 +325,7 @@ extern "C" int sb200_small_linear(void* handle, void* stream, const void* x, int
     SB200_REQUIRE(lora->down && lora->up && lora->r > 0 && lora->r <= kSlMaxR, "small_linear: lora rank");
     SB200_REQUIRE(lora->group_n >= kSlWarps * kSlColsPerWarp, "small_linear: lora group_n too small");
     a.down = static_cast<const __nv_bfloat16*>(lora->down);
-    a.up = static_cast<const __nv_bfloat16*>(lora->up);
+    a.up = static_cast<const float*>(lora->up);
     a.r = lora->r;
     a.group_n = lora->group_n;
     a.scale = lora->scale;

@@ -2,35 +2,47 @@
 //
 //   out[M, N] = epilogue( A[M, K] . W[N, K]^T  [+ scale * (A . down^T) . up^T] )
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer   — streams 128x64 A tiles and bn x 64 W tiles (+ the rt x 64 LoRA-down
-//                                 tile) through an mbarrier ring of shared-memory stages
-//   warp 1      MMA issuer     — one thread issues tcgen05.mma (UMMA 128 x bn x 16, bf16 -> fp32) into a
-//                                 double-buffered TMEM accumulator; the LoRA down-projection is a second
-//                                 128 x rt x 16 UMMA on the same A tile into spare TMEM columns
-//   warps 2..5  epilogue       — tcgen05.ld the accumulator (one row per thread), apply the rank-r LoRA
-//                                 up-projection, bias / time-embedding row bias / GEGLU / residual, store bf16
+// Persistent, warp-specialised kernel, one CTA per SM, in two flavours selected on the host:
+//   kCtas = 1   128 x bn output tile per CTA  (tcgen05.mma cta_group::1, UMMA 128 x bn x 16)
+//   kCtas = 2   256 x bn tile per CTA PAIR    (cluster of 2, cta_group::2, UMMA 256 x bn x 16): each CTA stages
+//               its own 128 A rows but only HALF of the W tile, which brings the shared-memory fill rate per SM
+//               (~70 B/clk measured) below the tensor-core rate for bn = 256 — the 1-CTA kernel is fill-bound.
+// Warp roles (320 threads):
+//   warp 0      TMA producer   — streams A / W (/ LoRA-down) tiles through an mbarrier ring of smem stages
+//   warp 1      MMA issuer     — one thread (leader CTA only) issues tcgen05.mma into a double-buffered TMEM
+//                                 accumulator; the LoRA down-projection is a second UMMA (N = rt) on the same A
+//                                 tile into spare TMEM columns
+//   warps 2..9  epilogue       — two warps per TMEM lane quarter, interleaved over 16-column chunks:
+//                                 tcgen05.ld (one row per thread), rank-r LoRA up-projection, bias / time-embedding
+//                                 row bias / GEGLU / residual; residual tiles come in by cp.async and results leave
+//                                 through a swizzled smem staging tile so that global accesses are coalesced
 //
-// The A operand has three addressing modes:
+// A-operand addressing modes:
 //   plain   2-D [M, K], optionally split along K over two sources (skip-connection concat, conv_shortcut)
 //   conv    4-D NHWC box per filter tap (implicit GEMM): the box start is shifted by (kh-1, kw-1) and TMA's
 //           out-of-bounds zero fill provides the padding; two sources along C give the concat
 //   conv/2  stride-2 conv: four parity-plane descriptors (even/odd rows x even/odd columns)
 //
-// Replaces (reference): every nn.Linear / nn.Conv2d leaf that diffusers' UNet2DConditionModel executes
-// under trainscripts/textsliders/train_util.py:242-247 together with the LoRA hook
-// trainscripts/textsliders/lora.py:108-112.
+// Replaces (reference): every nn.Linear / nn.Conv2d leaf that diffusers' UNet2DConditionModel executes under
+// trainscripts/textsliders/train_util.py:242-247 together with the LoRA hook trainscripts/textsliders/lora.py:108-112.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
 namespace sb200 {
 
-constexpr int kBM = 128;
+constexpr int kBM = 128;  // rows per CTA
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarRegion = 1024;
+constexpr int kSlab = 32;             // output columns staged per epilogue-warp iteration
+constexpr int kEpiBufBytes = 32 * 64; // [32 rows x 32 cols] bf16
+constexpr int kEpiBytesPerWarp = 2 * kEpiBufBytes;
+constexpr int kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
 
 struct GemmParams {
   CUtensorMap tmA[4];
@@ -40,10 +52,12 @@ struct GemmParams {
   int bn;           // accumulator tile width (UMMA N), multiple of 16
   int ncols_out;    // output columns per tile (bn, or bn/2 with GEGLU)
   int Nout;         // output columns overall (N, or N/2 with GEGLU)
-  int num_m_tiles, num_n_tiles;
+  int num_m_tiles, num_n_tiles;  // tiles of (128 * kCtas) x bn
   int kblocks;      // K / 64 (conv: 9 * cb_total)
   int stages;
-  int stage_bytes;  // bytes of one smem stage == expected TMA transaction bytes
+  int stage_bytes;  // bytes of one smem stage of ONE CTA
+  int b_rows;       // W rows staged per CTA per k-block (bn / kCtas)
+  int l_rows;       // LoRA-down rows staged per CTA (rt / kCtas)
   int a_mode;       // 0 plain, 1 conv3x3 stride 1, 2 conv3x3 stride 2
   int kb_split;     // k-blocks (per tap) that come from source 0
   int cb_total;     // k-blocks per tap
@@ -56,28 +70,38 @@ struct GemmParams {
   int ldr;
   __nv_bfloat16* out;
   int ldo;
-  const __nv_bfloat16* lora_up;
+  const float* lora_up;  // [N, r] fp32
   int lora_r, lora_rt, lora_group_n;
   float lora_scale;
   const float* lora_scale_dev;
 };
 
+__device__ __forceinline__ void add_bf16x16(float* f, const __nv_bfloat16* src) {
+  const uint4* bp = reinterpret_cast<const uint4*>(src);
+  const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+  const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f[2 * i] += bf16_lo(bw[i]);
+    f[2 * i + 1] += bf16_hi(bw[i]);
+  }
+}
+
 template <int R>
-__device__ __forceinline__ void lora_apply(float* f, const float* t, const __nv_bfloat16* up_rows) {
-  // up_rows: 16 consecutive rows of [N, R] bf16 (same address for the whole warp -> L1 broadcast)
+__device__ __forceinline__ void lora_apply(float* f, const float* t, const float* up_rows) {
+  // up_rows: 16 consecutive rows of [N, R] fp32 (same address for the whole warp -> L1 broadcast)
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    if constexpr (R == 4) {
-      uint2 u = __ldg(reinterpret_cast<const uint2*>(up_rows + i * 4));
-      f[i] += t[0] * bf16_lo(u.x) + t[1] * bf16_hi(u.x) + t[2] * bf16_lo(u.y) + t[3] * bf16_hi(u.y);
-    } else {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(up_rows + i * 8));
-      f[i] += t[0] * bf16_lo(u.x) + t[1] * bf16_hi(u.x) + t[2] * bf16_lo(u.y) + t[3] * bf16_hi(u.y) +
-              t[4] * bf16_lo(u.z) + t[5] * bf16_hi(u.z) + t[6] * bf16_lo(u.w) + t[7] * bf16_hi(u.w);
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(up_rows + i * R));
+    f[i] += t[0] * u0.x + t[1] * u0.y + t[2] * u0.z + t[3] * u0.w;
+    if constexpr (R == 8) {
+      const float4 u1 = __ldg(reinterpret_cast<const float4*>(up_rows + i * R + 4));
+      f[i] += t[4] * u1.x + t[5] * u1.y + t[6] * u1.z + t[7] * u1.w;
     }
   }
 }
 
+template <int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -86,11 +110,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const int S = p.stages;
-  const uint32_t bar_full = base;                 // S barriers
-  const uint32_t bar_empty = base + 8u * S;       // S barriers
-  const uint32_t bar_tfull = base + 16u * S;      // 2 barriers
-  const uint32_t bar_tempty = bar_tfull + 16u;    // 2 barriers
+  const uint32_t bar_full = base;                 // S barriers (used in the leader CTA)
+  const uint32_t bar_empty = base + 8u * S;       // S barriers (every CTA)
+  const uint32_t bar_tfull = base + 16u * S;      // 2 barriers (every CTA)
+  const uint32_t bar_tempty = bar_tfull + 16u;    // 2 barriers (used in the leader CTA)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 512);
   const uint32_t tiles = base + kBarRegion;
   const bool has_lora = (p.flags & SB200_EPI_LORA) != 0;
@@ -108,32 +134,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8u * i, 1);
-      mbar_init(bar_tempty + 8u * i, 4);
+      mbar_init(bar_tempty + 8u * i, kEpiWarps * kCtas);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-    tmem_relinquish();
+    if constexpr (kCtas == 2) {
+      tmem_alloc_2cta(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) {
+    cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int unit = blockIdx.x / kCtas;          // persistent work unit (CTA or CTA pair)
+  const int num_units = gridDim.x / kCtas;
   const uint32_t a_bytes = kBM * 128;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.b_rows) * 128;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (every CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit; t < total_tiles; t += num_units) {
         const int mt = t % p.num_m_tiles;
         const int nt = t / p.num_m_tiles;
-        const int m0 = mt * kBM;
+        const int m0 = (mt * kCtas + static_cast<int>(cta_rank)) * kBM;
         int b0 = 0, h0 = 0, w0 = 0;
         if (p.a_mode != 0) {
           const int hw = p.H * p.W;
@@ -142,16 +179,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           h0 = rem / p.W;
           w0 = rem - h0 * p.W;
         }
+        // W rows this CTA stages
+        int brow;
+        if (geglu) {
+          const int half = p.bn >> 1;
+          brow = kCtas == 2 ? (cta_rank == 0 ? nt * half : (p.N >> 1) + nt * half) : nt * half;
+        } else {
+          brow = nt * p.bn + static_cast<int>(cta_rank) * p.b_rows;
+        }
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
-          const uint32_t full = bar_full + 8u * stage;
-          mbar_expect_tx(full, static_cast<uint32_t>(p.stage_bytes));
+          uint32_t full = bar_full + 8u * stage;
+          if constexpr (kCtas == 2) {
+            // Both CTAs' TMA bytes are counted on the LEADER's barrier; only the leader arrives (expecting the
+            // bytes of the pair).  The peer's bytes for this stage cannot land before the previous use of the
+            // stage completed (its empty barrier is released by the leader's commit after that phase), and a
+            // transiently negative tx-count inside the right phase is legal.
+            full = mapa_u32(full, 0);
+            if (leader) mbar_expect_tx(bar_full + 8u * stage, static_cast<uint32_t>(p.stage_bytes) * 2u);
+          } else {
+            mbar_expect_tx(full, static_cast<uint32_t>(p.stage_bytes));
+          }
           const uint32_t sA = tiles + static_cast<uint32_t>(stage) * p.stage_bytes;
           const uint32_t sB = sA + a_bytes;
+          const CUtensorMap* amap;
+          int c0, c1, c2 = 0, c3 = 0;
           if (p.a_mode == 0) {
             const int src = kb < p.kb_split ? 0 : 1;
-            const int kc = (src ? kb - p.kb_split : kb) * kBK;
-            tma_load_2d(sA, &p.tmA[src], full, kc, m0);
+            amap = &p.tmA[src];
+            c0 = (src ? kb - p.kb_split : kb) * kBK;
+            c1 = m0;
           } else {
             const int tap = kb / p.cb_total;
             const int cb = kb - tap * p.cb_total;
@@ -159,27 +216,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             const int kw = tap - kh * 3;
             if (p.a_mode == 1) {
               const int src = cb < p.kb_split ? 0 : 1;
-              const int c0 = (src ? cb - p.kb_split : cb) * kBK;
-              tma_load_4d(sA, &p.tmA[src], full, c0, w0 + kw - 1, h0 + kh - 1, b0);
+              amap = &p.tmA[src];
+              c0 = (src ? cb - p.kb_split : cb) * kBK;
+              c1 = w0 + kw - 1;
+              c2 = h0 + kh - 1;
             } else {
               // input row 2*ho + kh - 1: kh=0 -> odd plane, row ho-1; kh=1 -> even plane, row ho;
               // kh=2 -> odd plane, row ho
               const int ph = (kh == 1) ? 0 : 1;
               const int pw = (kw == 1) ? 0 : 1;
-              const int dh = (kh == 0) ? -1 : 0;
-              const int dw = (kw == 0) ? -1 : 0;
-              tma_load_4d(sA, &p.tmA[ph * 2 + pw], full, cb * kBK, w0 + dw, h0 + dh, b0);
+              amap = &p.tmA[ph * 2 + pw];
+              c0 = cb * kBK;
+              c1 = w0 + ((kw == 0) ? -1 : 0);
+              c2 = h0 + ((kh == 0) ? -1 : 0);
             }
+            c3 = b0;
           }
-          if (geglu) {
-            const int half = p.bn >> 1;
-            tma_load_2d(sB, &p.tmB, full, kb * kBK, nt * half);
-            tma_load_2d(sB + static_cast<uint32_t>(half) * 128, &p.tmB, full, kb * kBK,
-                        (p.N >> 1) + nt * half);
+          if constexpr (kCtas == 2) {
+            if (p.a_mode == 0)
+              tma_load_2d_2cta(sA, amap, full, c0, c1);
+            else
+              tma_load_4d_2cta(sA, amap, full, c0, c1, c2, c3);
+            tma_load_2d_2cta(sB, &p.tmB, full, kb * kBK, brow);
+            if (has_lora) tma_load_2d_2cta(sB + b_bytes, &p.tmL, full, kb * kBK, static_cast<int>(cta_rank) * p.l_rows);
           } else {
-            tma_load_2d(sB, &p.tmB, full, kb * kBK, nt * p.bn);
+            if (p.a_mode == 0)
+              tma_load_2d(sA, amap, full, c0, c1);
+            else
+              tma_load_4d(sA, amap, full, c0, c1, c2, c3);
+            tma_load_2d(sB, &p.tmB, full, kb * kBK, brow);
+            if (geglu)
+              tma_load_2d(sB + static_cast<uint32_t>(p.bn >> 1) * 128, &p.tmB, full, kb * kBK,
+                          (p.N >> 1) + nt * (p.bn >> 1));
+            if (has_lora) tma_load_2d(sB + b_bytes, &p.tmL, full, kb * kBK, 0);
           }
-          if (has_lora) tma_load_2d(sB + b_bytes, &p.tmL, full, kb * kBK, 0);
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -188,15 +258,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBM, p.bn);
-      const uint32_t idesc_l = umma_idesc_bf16(kBM, has_lora ? p.lora_rt : 16);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(kBM * kCtas, p.bn);
+      const uint32_t idesc_l = umma_idesc_bf16(kBM * kCtas, has_lora ? p.lora_rt : 16);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit; t < total_tiles; t += num_units) {
         mbar_wait(bar_tempty + 8u * as, aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
@@ -211,14 +281,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             const uint64_t adesc = umma_desc_sw128(sA + k * 32);
             const uint64_t bdesc = umma_desc_sw128(sB + k * 32);
             const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-            umma_ss(d_tmem, adesc, bdesc, idesc, acc);
-            if (has_lora) {
-              const uint64_t ldesc = umma_desc_sw128(sL + k * 32);
-              umma_ss(d_tmem + static_cast<uint32_t>(p.bn), adesc, ldesc, idesc_l, acc);
+            if constexpr (kCtas == 2) {
+              umma_ss_2cta(d_tmem, adesc, bdesc, idesc, acc);
+              if (has_lora)
+                umma_ss_2cta(d_tmem + static_cast<uint32_t>(p.bn), adesc, umma_desc_sw128(sL + k * 32), idesc_l, acc);
+            } else {
+              umma_ss(d_tmem, adesc, bdesc, idesc, acc);
+              if (has_lora)
+                umma_ss(d_tmem + static_cast<uint32_t>(p.bn), adesc, umma_desc_sw128(sL + k * 32), idesc_l, acc);
             }
           }
-          umma_commit(bar_empty + 8u * stage);  // frees the smem stage once these MMAs retire
-          if (kb == p.kblocks - 1) umma_commit(bar_tfull + 8u * as);
+          // free the smem stage (in every CTA of the pair) once these MMAs retire
+          if constexpr (kCtas == 2) {
+            umma_commit_2cta(bar_empty + 8u * stage, 3);
+            if (kb == p.kblocks - 1) umma_commit_2cta(bar_tfull + 8u * as, 3);
+          } else {
+            umma_commit(bar_empty + 8u * stage);
+            if (kb == p.kblocks - 1) umma_commit(bar_tfull + 8u * as);
+          }
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -229,185 +309,288 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9, every CTA)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hsel = (warp - 2) >> 2;       // which of the two warps of this quarter (chunk parity)
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const float lscale =
+        has_lora ? (p.lora_scale_dev ? p.lora_scale * __ldg(p.lora_scale_dev) : p.lora_scale) : 0.f;
+    const bool has_resid = (p.flags & SB200_EPI_RESID) != 0;
+    const uint32_t tempty_leader = kCtas == 2 ? mapa_u32(bar_tempty, 0) : bar_tempty;
+    // per-warp staging buffers (2 x [32 rows x 32 cols] bf16, 64 B rows, 16-byte chunks XOR-swizzled by
+    // (row >> 1) & 3): residual tiles arrive here by cp.async with coalesced global reads, results leave from
+    // here with coalesced global writes; in between every thread touches only its own row.
+    const uint32_t ebuf = tiles + static_cast<uint32_t>(S) * p.stage_bytes + static_cast<uint32_t>(warp - 2) * kEpiBytesPerWarp;
+    int bufsel = 0;
+    for (int t = unit; t < total_tiles; t += num_units) {
       const int mt = t % p.num_m_tiles;
       const int nt = t / p.num_m_tiles;
-      mbar_wait(bar_tfull + 8u * as, aphase);
-      tc_fence_after();
-      const int m = mt * kBM + q * 32 + lane;
+      const int m_q = (mt * kCtas + static_cast<int>(cta_rank)) * kBM + q * 32;  // first row of this warp
+      const int m = m_q + lane;
       const bool row_ok = m < p.M;
-      const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
       const int n_base = nt * p.ncols_out;
+      const int ncols_valid = min(p.ncols_out, p.Nout - n_base);
+      const int nslabs = (ncols_valid + kSlab - 1) / kSlab;
+      const int my_slabs = (nslabs - hsel + 1) >> 1;  // slabs hsel, hsel+2, ...
+      auto prefetch_resid = [&](int col0, int sw, uint32_t buf) {
+        const int cpr = sw >> 3;  // 16-byte chunks per row
+        for (int idx = lane; idx < 32 * cpr; idx += 32) {
+          const int row = idx / cpr;
+          const int ch = idx - row * cpr;
+          const int mr = m_q + row;
+          if (mr < p.M)
+            cp_async_16(buf + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4),
+                        p.resid + static_cast<size_t>(mr) * p.ldr + n_base + col0 + ch * 8);
+        }
+        cp_async_commit();
+      };
+      if (has_resid && my_slabs > 0)
+        prefetch_resid(hsel * kSlab, min(kSlab, ncols_valid - hsel * kSlab), ebuf + bufsel * kEpiBufBytes);
       const __nv_bfloat16* rb =
           (p.flags & SB200_EPI_ROWBIAS)
               ? p.rowbias + static_cast<size_t>(row_ok ? m / p.rows_per_batch : 0) * p.Nout
               : nullptr;
+      mbar_wait(bar_tfull + 8u * as, aphase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
       float tl[8];
       int cur_group = -1;
-      const float lscale =
-          has_lora ? (p.lora_scale_dev ? p.lora_scale * __ldg(p.lora_scale_dev) : p.lora_scale) : 0.f;
-      for (int c = 0; c < p.ncols_out; c += 16) {
-        const int n = n_base + c;
-        if (n >= p.Nout) break;  // warp-uniform
-        uint32_t v[16];
-        uint32_t g[16];
-        tmem_ld_x16(taddr + c, v);
-        if (geglu) tmem_ld_x16(taddr + (p.bn >> 1) + c, g);
-        if (has_lora) {
-          const int grp = n / p.lora_group_n;
-          if (grp != cur_group) {
-            cur_group = grp;
-            uint32_t tv[8];
-            tmem_ld_x8(taddr + p.bn + grp * p.lora_r, tv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tl[j] = __uint_as_float(tv[j]) * lscale;
-          }
+      const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);
+      for (int k = 0; k < my_slabs; ++k) {
+        const int col0 = (hsel + 2 * k) * kSlab;
+        const int sw = min(kSlab, ncols_valid - col0);
+        const uint32_t buf = ebuf + bufsel * kEpiBufBytes;
+        const bool more = k + 1 < my_slabs;
+        if (has_resid && more) {
+          const int ncol0 = col0 + 2 * kSlab;
+          prefetch_resid(ncol0, min(kSlab, ncols_valid - ncol0), ebuf + (bufsel ^ 1) * kEpiBufBytes);
         }
-        tmem_ld_wait();
-        float f[16];
+        for (int sub = 0; sub * 16 < sw; ++sub) {
+          const int c = col0 + sub * 16;
+          const int n = n_base + c;
+          uint32_t v[16];
+          uint32_t g[16];
+          tmem_ld_x16(taddr + c, v);
+          if (geglu) tmem_ld_x16(taddr + (p.bn >> 1) + c, g);
+          if (has_lora) {
+            const int grp = n / p.lora_group_n;
+            if (grp != cur_group) {
+              cur_group = grp;
+              uint32_t tv[8];
+              tmem_ld_x8(taddr + p.bn + grp * p.lora_r, tv);
+              tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        if (has_lora) {
-          const __nv_bfloat16* up = p.lora_up + static_cast<size_t>(n) * p.lora_r;
-          if (p.lora_r == 4)
-            lora_apply<4>(f, tl, up);
-          else
-            lora_apply<8>(f, tl, up);
-        }
-        if (p.flags & SB200_EPI_BIAS) {
-          const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n);
-          const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-          const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            f[2 * i] += bf16_lo(bw[i]);
-            f[2 * i + 1] += bf16_hi(bw[i]);
-          }
-        }
-        if (rb) {
-          const uint4* bp = reinterpret_cast<const uint4*>(rb + n);
-          const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-          const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            f[2 * i] += bf16_lo(bw[i]);
-            f[2 * i + 1] += bf16_hi(bw[i]);
-          }
-        }
-        if (geglu) {
-          float gb[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gb[i] = 0.f;
-          if (p.flags & SB200_EPI_BIAS) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + p.Nout + n);
-            const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-            const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              gb[2 * i] = bf16_lo(bw[i]);
-              gb[2 * i + 1] = bf16_hi(bw[i]);
+              for (int j = 0; j < 8; ++j) tl[j] = __uint_as_float(tv[j]) * lscale;
             }
           }
+          tmem_ld_wait();
+          float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] *= gelu_erf_f(__uint_as_float(g[i]) + gb[i]);
-        }
-        if (row_ok) {
-          if (p.flags & SB200_EPI_RESID) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + static_cast<size_t>(m) * p.ldr + n);
-            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (has_lora) {
+            const float* up = p.lora_up + static_cast<size_t>(n) * p.lora_r;
+            if (p.lora_r == 4)
+              lora_apply<4>(f, tl, up);
+            else
+              lora_apply<8>(f, tl, up);
+          }
+          if (p.flags & SB200_EPI_BIAS) add_bf16x16(f, p.bias + n);
+          if (rb) add_bf16x16(f, rb + n);
+          if (geglu) {
+            float gb[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gb[j] = __uint_as_float(g[j]);
+            if (p.flags & SB200_EPI_BIAS) add_bf16x16(gb, p.bias + p.Nout + n);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_f(gb[j]);
+          }
+          const uint32_t a0 = buf + lane * 64 + (((2 * sub) ^ swz) << 4);
+          const uint32_t a1 = buf + lane * 64 + (((2 * sub + 1) ^ swz) << 4);
+          if (has_resid) {
+            if (sub == 0) {  // this slab's residual has landed (the next slab's copy may still be in flight)
+              if (more)
+                cp_async_wait<1>();
+              else
+                cp_async_wait<0>();
+              __syncwarp();
+            }
+            const uint4 r0 = ld_shared_v4(a0), r1 = ld_shared_v4(a1);
             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[2 * i] += bf16_lo(rw[i]);
-              f[2 * i + 1] += bf16_hi(rw[i]);
+            for (int j = 0; j < 8; ++j) {
+              f[2 * j] += bf16_lo(rw[j]);
+              f[2 * j + 1] += bf16_hi(rw[j]);
             }
           }
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(f[0], f[1]);
-          o0.y = pack_bf16x2(f[2], f[3]);
-          o0.z = pack_bf16x2(f[4], f[5]);
-          o0.w = pack_bf16x2(f[6], f[7]);
-          o1.x = pack_bf16x2(f[8], f[9]);
-          o1.y = pack_bf16x2(f[10], f[11]);
-          o1.z = pack_bf16x2(f[12], f[13]);
-          o1.w = pack_bf16x2(f[14], f[15]);
-          uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + n);
-          op[0] = o0;
-          op[1] = o1;
+          st_shared_v4(a0, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                      pack_bf16x2(f[6], f[7])));
+          st_shared_v4(a1, make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                                      pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15])));
+        }
+        if (!more) {
+          // the accumulator has been read completely: hand it back to the MMA warp before the last copy-out
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtas == 2)
+              mbar_arrive_cluster(tempty_leader + 8u * as);
+            else
+              mbar_arrive(bar_tempty + 8u * as);
+          }
+        }
+        __syncwarp();
+        {  // coalesced copy-out of the staged [32 x sw] tile
+          const int cpr = sw >> 3;
+          for (int idx = lane; idx < 32 * cpr; idx += 32) {
+            const int row = idx / cpr;
+            const int ch = idx - row * cpr;
+            const int mr = m_q + row;
+            const uint4 val = ld_shared_v4(buf + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+            if (mr < p.M)
+              *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(mr) * p.ldo + n_base + col0 + ch * 8) = val;
+          }
+        }
+        __syncwarp();
+        bufsel ^= 1;
+      }
+      if (my_slabs == 0) {  // nothing to read for this warp (narrow last tile): still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtas == 2)
+            mbar_arrive_cluster(tempty_leader + 8u * as);
+          else
+            mbar_arrive(bar_tempty + 8u * as);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8u * as);
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
   }
 
+  __syncwarp();  // reconverge the single-lane roles before the block / cluster barrier
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) {
+    cluster_sync_all();  // the peer's barriers / smem must outlive every multicast arrive aimed at them
+  } else {
+    __syncthreads();
+  }
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (kCtas == 2)
+      tmem_dealloc_2cta(tmem_base, 512);
+    else
+      tmem_dealloc(tmem_base, 512);
   }
 }
 
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
-static int pick_bn(int m_tiles, int n_cols, int max_bn, int step, int num_sms, int kblocks) {
-  // minimise waves x (tile time); tile time ~ kblocks * max(bn, 64) cycles*2 + a fixed per-tile cost
-  long best_cost = -1;
-  int best = step;
-  for (int bn = step; bn <= max_bn; bn += step) {
-    const int n_tiles = (n_cols + bn - 1) / bn;
-    const long tiles = static_cast<long>(m_tiles) * n_tiles;
-    const long waves = (tiles + num_sms - 1) / num_sms;
-    const long tile_cost = static_cast<long>(kblocks) * (bn > 96 ? bn : 96) + 600;
-    const long cost = waves * tile_cost;
-    if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best)) {
-      best_cost = cost;
-      best = bn;
+struct TileChoice {
+  int ctas;
+  int bn;
+};
+
+// Cost model (cycles) fitted to ncu captures (profiles/r01_*): the tensor pipe needs 2*bn clk per 64-deep k-block
+// of a 128-row (per CTA) tile; a CTA can fill shared memory at ~70 B/clk; work is dealt in waves over the
+// persistent units; each launch pays a fixed prologue and the last tile's epilogue.
+static TileChoice pick_tile(int M, int ncols, int max_bn, int step, int num_sms, int kblocks, int lora_rt,
+                            bool allow_pair, int force_ctas) {
+  double best = -1;
+  TileChoice bc{1, step};
+  for (int ctas = 1; ctas <= (allow_pair ? 2 : 1); ++ctas) {
+    if (force_ctas && ctas != force_ctas) continue;
+    const int m_tiles = (M + kBM * ctas - 1) / (kBM * ctas);
+    const int units = num_sms / ctas;
+    for (int bn = step; bn <= max_bn; bn += step) {
+      if (ctas == 2 && (bn % 32 != 0 && step == 32)) continue;
+      const int n_tiles = (ncols + bn - 1) / bn;
+      const long tiles = static_cast<long>(m_tiles) * n_tiles;
+      const long waves = (tiles + units - 1) / units;
+      const double mma = 2.0 * (bn + (lora_rt ? 16 : 0));
+      const double fill = (16384.0 + (bn + lora_rt) * 128.0 / ctas) / 70.0;
+      const double perkb = mma > fill ? mma : fill;
+      const double epi = 300.0 + bn * 10.0;  // per tile, overlapped with the next tile's main loop
+      const double tile = kblocks * perkb > epi ? kblocks * perkb : epi;
+      const double cost = waves * tile + 4000.0 + epi;
+      if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && bn > bc.bn)) {
+        best = cost;
+        bc = TileChoice{ctas, bn};
+      }
     }
   }
-  return best;
+  return bc;
 }
 
-static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p) {
-  const int lora_bytes = (p.flags & SB200_EPI_LORA) ? p.lora_rt * 128 : 0;
-  p.stage_bytes = kBM * 128 + p.bn * 128 + lora_bytes;
-  int stages = (kSmemBudget - kBarRegion - 1024) / p.stage_bytes;
+// The CTA-pair kernel is correct (tests force it) but measured no faster than the single-CTA kernel on B200 so
+// far (profiles/README.md), so the automatic choice uses it only when SB200_ALLOW_PAIR=1.
+static bool pair_allowed() {
+  static const bool v = [] {
+    const char* e = getenv("SB200_ALLOW_PAIR");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
+static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
+  const bool has_lora = p.flags & SB200_EPI_LORA;
+  p.b_rows = p.bn / ctas;
+  p.l_rows = has_lora ? p.lora_rt / ctas : 0;
+  p.stage_bytes = kBM * 128 + p.b_rows * 128 + p.l_rows * 128;
+  int stages = (kSmemBudget - kBarRegion - 1024 - kEpiBytes) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(SB200_ERR_INVALID, "gemm: tile does not fit shared memory");
   p.stages = stages;
-  const int smem = kBarRegion + 1024 + stages * p.stage_bytes;
+  const int smem = kBarRegion + 1024 + stages * p.stage_bytes + kEpiBytes;
   if (!ctx->gemm_attr_set) {
-    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kSmemBudget));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     ctx->gemm_attr_set = true;
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
-  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(p);
+  if (ctas == 1) {
+    const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+    gemm_kernel<1><<<grid, kGemmThreads, smem, stream>>>(p);
+  } else {
+    const int units = ctx->num_sms / 2;
+    const int grid = 2 * (total < units ? total : units);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    SB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<2>, p));
+  }
   SB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-static int check_lora(const sb200_lora* l, int N, int max_rt) {
+static int check_lora(const sb200_lora* l, int N) {
   SB200_REQUIRE(l->down && l->up, "lora: NULL weights");
   SB200_REQUIRE(l->r == 4 || l->r == 8, "lora: rank %d unsupported by the fused epilogue (4 or 8)", l->r);
   SB200_REQUIRE(l->rt == 16 || l->rt == 32, "lora: rt must be 16 or 32");
   SB200_REQUIRE(l->group_n > 0 && l->group_n % 16 == 0, "lora: group_n must be a multiple of 16");
   const int groups = (N + l->group_n - 1) / l->group_n;
   SB200_REQUIRE(groups * l->r <= l->rt, "lora: %d groups of rank %d exceed rt=%d", groups, l->r, l->rt);
-  (void)max_rt;
   return 0;
+}
+
+// bn encodes an explicit choice when > 0: low 12 bits = tile width, bit 12 set = force the CTA-pair kernel,
+// bit 13 set = force the single-CTA kernel (used by the tests to cover both).
+static void decode_bn(int bn_arg, int* bn, int* force_ctas) {
+  *force_ctas = (bn_arg > 0 && (bn_arg & 0x1000)) ? 2 : ((bn_arg > 0 && (bn_arg & 0x2000)) ? 1 : 0);
+  *bn = bn_arg > 0 ? (bn_arg & 0xFFF) : 0;
 }
 
 }  // namespace sb200
@@ -417,7 +600,7 @@ using namespace sb200;
 extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, const void* x1, int ldx1,
                           int K0, const void* w, int ldw, void* out, int ldo, int M, int N, int K,
                           int flags, const void* bias, const void* rowbias, int rows_per_batch,
-                          const void* resid, int ldr, const sb200_lora* lora, int bn) {
+                          const void* resid, int ldr, const sb200_lora* lora, int bn_arg) {
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "gemm: NULL handle");
   SB200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad dims M=%d N=%d K=%d", M, N, K);
@@ -444,17 +627,16 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
   p.K = K;
   p.flags = flags;
   p.Nout = geglu ? N / 2 : N;
-  p.num_m_tiles = (M + kBM - 1) / kBM;
   p.kblocks = (K + kBK - 1) / kBK;
   p.a_mode = 0;
   p.kb_split = split ? K0 / kBK : p.kblocks;
   p.cb_total = p.kblocks;
   int max_bn = 256;
   if (has_lora) {
-    int st = check_lora(lora, N, 32);
+    int st = check_lora(lora, N);
     if (st) return st;
     max_bn = 256 - lora->rt;
-    p.lora_up = static_cast<const __nv_bfloat16*>(lora->up);
+    p.lora_up = static_cast<const float*>(lora->up);
     p.lora_r = lora->r;
     p.lora_rt = lora->rt;
     p.lora_group_n = lora->group_n;
@@ -462,13 +644,16 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
     p.lora_scale_dev = lora->scale_dev;
   }
   const int step = geglu ? 32 : 16;
-  if (bn <= 0) {
-    bn = pick_bn(p.num_m_tiles, geglu ? N : N, max_bn, step, ctx->num_sms, p.kblocks);
-  }
-  SB200_REQUIRE(bn % step == 0 && bn >= step && bn <= max_bn, "gemm: bn=%d invalid (step %d, max %d)", bn,
-                step, max_bn);
-  p.bn = bn;
-  p.ncols_out = geglu ? bn / 2 : bn;
+  int bn, force_ctas;
+  decode_bn(bn_arg, &bn, &force_ctas);
+  TileChoice tc = pick_tile(M, N, max_bn, step, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, pair_allowed(), force_ctas);
+  if (bn > 0) tc.bn = bn;
+  if (force_ctas) tc.ctas = force_ctas;
+  SB200_REQUIRE(tc.bn % step == 0 && tc.bn >= step && tc.bn <= max_bn, "gemm: bn=%d invalid (step %d, max %d)",
+                tc.bn, step, max_bn);
+  p.bn = tc.bn;
+  p.ncols_out = geglu ? tc.bn / 2 : tc.bn;
+  p.num_m_tiles = (M + kBM * tc.ctas - 1) / (kBM * tc.ctas);
   p.num_n_tiles = (p.Nout + p.ncols_out - 1) / p.ncols_out;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.rowbias = static_cast<const __nv_bfloat16*>(rowbias);
@@ -494,23 +679,24 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {kBK, static_cast<uint32_t>(geglu ? bn / 2 : bn)};
+    const int brows = (geglu || tc.ctas == 2) ? tc.bn / 2 : tc.bn;
+    const uint32_t box[2] = {kBK, static_cast<uint32_t>(brows)};
     if ((st = make_tmap_bf16(ctx, &p.tmB, w, 2, dims, strides, box))) return st;
   }
   if (has_lora) {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(lora->rt)};
     const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-    const uint32_t box[2] = {kBK, static_cast<uint32_t>(lora->rt)};
+    const uint32_t box[2] = {kBK, static_cast<uint32_t>(lora->rt / tc.ctas)};
     if ((st = make_tmap_bf16(ctx, &p.tmL, lora->down, 2, dims, strides, box))) return st;
   }
-  return launch_gemm(ctx, static_cast<cudaStream_t>(stream), p);
+  return launch_gemm(ctx, static_cast<cudaStream_t>(stream), p, tc.ctas);
 }
 
 extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx0, const void* x1,
                              int ldx1, int C0, int C1, const void* w, void* out, int ldo, int B, int Hin,
                              int Win, int Cout, int stride, int flags, const void* bias,
                              const void* rowbias, const void* resid, int ldr, const sb200_lora* lora,
-                             int bn) {
+                             int bn_arg) {
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "conv3x3: NULL handle");
   SB200_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride %d", stride);
@@ -528,7 +714,7 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
   SB200_REQUIRE(!(flags & SB200_EPI_ROWBIAS) || rowbias, "conv3x3: ROWBIAS without rowbias");
   SB200_REQUIRE(!(flags & SB200_EPI_RESID) || (resid && ldr % 8 == 0), "conv3x3: RESID args");
   const int H = Hin / stride, W = Win / stride;
-  // 128 output pixels per tile = bb images x bh rows x bw columns, contiguous in NHWC order
+  // 128 output pixels per CTA tile = bb images x bh rows x bw columns, contiguous in NHWC order
   int bw, bh, bb;
   if (W >= 128) {
     SB200_REQUIRE(W % 128 == 0, "conv3x3: W=%d must be a multiple of 128 or divide 128", W);
@@ -555,7 +741,6 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
   p.K = 9 * Cin;
   p.flags = flags;
   p.Nout = Cout;
-  p.num_m_tiles = (M + kBM - 1) / kBM;
   p.cb_total = Cin / kBK;
   p.kblocks = 9 * p.cb_total;
   p.a_mode = stride == 1 ? 1 : 2;
@@ -564,21 +749,26 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
   p.W = W;
   int max_bn = 256;
   if (has_lora) {
-    int st = check_lora(lora, Cout, 32);
+    int st = check_lora(lora, Cout);
     if (st) return st;
     max_bn = 256 - lora->rt;
-    p.lora_up = static_cast<const __nv_bfloat16*>(lora->up);
+    p.lora_up = static_cast<const float*>(lora->up);
     p.lora_r = lora->r;
     p.lora_rt = lora->rt;
     p.lora_group_n = lora->group_n;
     p.lora_scale = lora->scale;
     p.lora_scale_dev = lora->scale_dev;
   }
-  if (bn <= 0) bn = pick_bn(p.num_m_tiles, Cout, max_bn, 16, ctx->num_sms, p.kblocks);
-  SB200_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= max_bn, "conv3x3: bn=%d invalid", bn);
-  p.bn = bn;
-  p.ncols_out = bn;
-  p.num_n_tiles = (Cout + bn - 1) / bn;
+  int bn, force_ctas;
+  decode_bn(bn_arg, &bn, &force_ctas);
+  TileChoice tc = pick_tile(M, Cout, max_bn, 16, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, pair_allowed(), force_ctas);
+  if (bn > 0) tc.bn = bn;
+  if (force_ctas) tc.ctas = force_ctas;
+  SB200_REQUIRE(tc.bn % 16 == 0 && tc.bn >= 16 && tc.bn <= max_bn, "conv3x3: bn=%d invalid", tc.bn);
+  p.bn = tc.bn;
+  p.ncols_out = tc.bn;
+  p.num_m_tiles = (M + kBM * tc.ctas - 1) / (kBM * tc.ctas);
+  p.num_n_tiles = (Cout + tc.bn - 1) / tc.bn;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.rowbias = static_cast<const __nv_bfloat16*>(rowbias);
   p.rows_per_batch = H * W;
@@ -616,14 +806,14 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(Cout)};
     const uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
-    const uint32_t wbox[2] = {kBK, static_cast<uint32_t>(bn)};
+    const uint32_t wbox[2] = {kBK, static_cast<uint32_t>(tc.bn / tc.ctas)};
     if ((st = make_tmap_bf16(ctx, &p.tmB, w, 2, dims, strides, wbox))) return st;
   }
   if (has_lora) {
     const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(lora->rt)};
     const uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
-    const uint32_t lbox[2] = {kBK, static_cast<uint32_t>(lora->rt)};
+    const uint32_t lbox[2] = {kBK, static_cast<uint32_t>(lora->rt / tc.ctas)};
     if ((st = make_tmap_bf16(ctx, &p.tmL, lora->down, 2, dims, strides, lbox))) return st;
   }
-  return launch_gemm(ctx, static_cast<cudaStream_t>(stream), p);
+  return launch_gemm(ctx, static_cast<cudaStream_t>(stream), p, tc.ctas);
 }

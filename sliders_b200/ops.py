@@ -166,8 +166,9 @@ def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
     return out
 
 
-def small_linear(x: torch.Tensor, w: torch.Tensor, bias=None, *, act_in: bool = False, act_out: bool = False,
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias=None, *, act_in: bool = False, act_out: int = 0,
                  lora: Optional[Lora] = None, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act_out: 0 none, 1 SiLU(y) + resid, 2 SiLU(bf16(y + resid)) — see sb200_small_linear."""
     M, K = x.shape
     N = w.shape[0]
     out = torch.empty((M, N), device=x.device, dtype=BF16)

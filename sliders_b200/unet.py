@@ -390,7 +390,7 @@ class UNet2DConditionModel(nn.Module):
             N = sum(l.weight.shape[0] for l in leaves)
             if pack.down is None:
                 pack.down = torch.zeros((rt, K), device=dev, dtype=BF16)
-                pack.up = torch.zeros((N, r), device=dev, dtype=BF16)
+                pack.up = torch.zeros((N, r), device=dev, dtype=torch.float32)  # sb200_lora.up is fp32
             else:
                 pack.down.zero_()
                 pack.up.zero_()
@@ -419,12 +419,12 @@ class UNet2DConditionModel(nn.Module):
     _capturing = False
 
     # ---- forward pieces ------------------------------------------------------------------------------
-    def _resnet(self, blk: ResnetBlock2D, x0, x1, emb_act_in) -> torch.Tensor:
-        """x0 (and optional skip x1): [B,H,W,C*] NHWC.  emb: [B, 1280] (SiLU applied inside small_linear)."""
+    def _resnet(self, blk: ResnetBlock2D, x0, x1, emb_act) -> torch.Tensor:
+        """x0 (and optional skip x1): [B,H,W,C*] NHWC.  emb_act: SiLU(emb) [B, 1280]."""
         B, H, W, _ = x0.shape
         n1 = blk.norm1
         h = ops.groupnorm(x0, self._w_norm(n1)[0], self._w_norm(n1)[1], n1.num_groups, n1.eps, True, x1=x1)
-        temb = ops.small_linear(emb_act_in, self._w(blk.time_emb_proj), self._b(blk.time_emb_proj), act_in=True,
+        temb = ops.small_linear(emb_act, self._w(blk.time_emb_proj), self._b(blk.time_emb_proj),
                                 lora=self._lora([blk.time_emb_proj]))
         h = ops.conv3x3(h, self._w(blk.conv1), bias=self._b(blk.conv1), rowbias=temb, lora=self._lora([blk.conv1]))
         n2 = blk.norm2
@@ -487,12 +487,14 @@ class UNet2DConditionModel(nn.Module):
         return h.view(B, H, W, C_)
 
     def _embeddings(self, timesteps_f32, B, added_cond_kwargs):
-        """Returns emb [B, temb] (pre-SiLU; every resnet applies SiLU in its time_emb_proj load)."""
+        """Returns SiLU(emb) [B, temb].  In diffusers `emb` has exactly one kind of consumer — every
+        ResnetBlock2D's `time_emb_proj(nonlinearity(emb))` — so the activation is applied once here."""
         te = self.time_embedding
         t_emb = ops.sinusoid(timesteps_f32, self.time_proj.num_channels)
-        h = ops.small_linear(t_emb, self._w(te.linear_1), self._b(te.linear_1), act_out=True)
-        emb = ops.small_linear(h, self._w(te.linear_2), self._b(te.linear_2))
-        if getattr(self.config, "addition_embed_type", None) == "text_time":
+        h = ops.small_linear(t_emb, self._w(te.linear_1), self._b(te.linear_1), act_out=1)
+        text_time = getattr(self.config, "addition_embed_type", None) == "text_time"
+        emb = ops.small_linear(h, self._w(te.linear_2), self._b(te.linear_2), act_out=0 if text_time else 2)
+        if text_time:
             if added_cond_kwargs is None or "text_embeds" not in added_cond_kwargs or "time_ids" not in added_cond_kwargs:
                 raise ValueError("addition_embed_type 'text_time' needs added_cond_kwargs['text_embeds','time_ids']")
             text_embeds = added_cond_kwargs["text_embeds"].to(device=emb.device, dtype=BF16)
@@ -500,8 +502,8 @@ class UNet2DConditionModel(nn.Module):
             tid = ops.sinusoid(time_ids.reshape(-1).contiguous(), self.add_time_proj.num_channels)
             add = torch.cat([text_embeds, tid.view(B, -1)], dim=-1).contiguous()
             ae = self.add_embedding
-            a = ops.small_linear(add, self._w(ae.linear_1), self._b(ae.linear_1), act_out=True)
-            emb = ops.small_linear(a, self._w(ae.linear_2), self._b(ae.linear_2), resid=emb)
+            a = ops.small_linear(add, self._w(ae.linear_1), self._b(ae.linear_1), act_out=1)
+            emb = ops.small_linear(a, self._w(ae.linear_2), self._b(ae.linear_2), resid=emb, act_out=2)
         return emb
 
     def _forward_impl(self, sample, timesteps_f32, ehs, added_cond_kwargs, out_dtype):

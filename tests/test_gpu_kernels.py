@@ -1,0 +1,300 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (sliders_b200.ops) and compared
+with fp32 torch math on the same bf16 inputs.  Tolerances: outputs are bf16 (relative rounding 2^-9 = 0.2 %), so
+rel-RMS <= 1e-2 catches any indexing / accumulation error while allowing output rounding; attention additionally
+rounds P to bf16 (standard flash attention), tolerance 2e-2.  Both GEMM kernels (single-CTA and the cta_group::2
+CTA-pair) are forced explicitly."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+SINGLE, PAIR = 0x2000, 0x1000
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def rel_rms(got, ref):
+    got, ref = got.float(), ref.float()
+    assert torch.isfinite(got).all()
+    return ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+
+
+def make_lora(K, N, r, group_n, dev, seed, conv_cin=None):
+    from sliders_b200.ops import Lora
+
+    g = torch.Generator().manual_seed(seed)
+    groups = (N + group_n - 1) // group_n
+    rt = 16 if groups * r <= 16 else 32
+    down = torch.zeros(rt, K)
+    down[: groups * r] = torch.randn(groups * r, K, generator=g) / K ** 0.5
+    up = (torch.randn(N, r, generator=g) * 0.5).to(BF).float()
+    down = down.to(dev, BF)
+    up = up.to(dev)
+    return down, up, rt
+
+
+@pytest.mark.parametrize("force", [SINGLE, PAIR, 0])
+@pytest.mark.parametrize("M,N,K,flags,split,lora", [
+    (128, 64, 64, "", 0, None),                 # one tile, one k-block
+    (1000, 640, 640, "bR", 0, None),            # ragged M, bias + residual
+    (154, 1280, 2048, "", 0, None),             # cross-attention K/V projection shape (77 x 2)
+    (2048, 2560, 640, "bG", 0, None),           # GEGLU
+    (1024, 640, 1920, "b", 1280, None),         # skip-concat split K (conv_shortcut)
+    (1024, 1280, 1280, "bL", 0, (4, 1280, 0.25)),
+    (1024, 1920, 640, "L", 0, (4, 640, 1.0)),   # fused to_q|to_k|to_v, three adaptors
+    (512, 640, 640, "bRL", 0, (8, 640, -2.0)),  # rank 8, negative slider
+    (4096, 1280, 1280, "btR", 0, None),         # row bias (time embedding) + residual
+])
+def test_gemm(dev, force, M, N, K, flags, split, lora):
+    from sliders_b200 import ops
+
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(dev, BF)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev, BF)
+    geglu = "G" in flags
+    nout = N // 2 if geglu else N
+    bias = torch.randn(N, generator=g).to(dev, BF) if "b" in flags else None
+    rpb = max(1, M // 4)
+    rowbias = torch.randn((M + rpb - 1) // rpb, nout, generator=g).to(dev, BF) if "t" in flags else None
+    resid = torch.randn(M, nout, generator=g).to(dev, BF) if "R" in flags else None
+    la = None
+    if lora:
+        r, group_n, scale = lora
+        down, up, rt = make_lora(K, N, r, group_n, dev, 7)
+        la = ops.Lora(down, up, r, group_n, scale)
+    x0, x1 = (x[:, :split].contiguous(), x[:, split:].contiguous()) if split else (x, None)
+    out = ops.gemm(x0, w, bias=bias, rowbias=rowbias, rows_per_batch=rpb, resid=resid, geglu=geglu, lora=la, x1=x1,
+                   bn=force)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t()
+    if lora:
+        t = x.float() @ down.float().t()
+        for g0 in range(0, N, group_n):
+            grp = g0 // group_n
+            ref[:, g0:g0 + group_n] += (t[:, grp * r:(grp + 1) * r] @ up[g0:g0 + group_n].t()) * scale
+    if bias is not None:
+        ref = ref + bias.float()
+    if geglu:
+        a, gate = ref.chunk(2, dim=-1)
+        ref = a * F.gelu(gate)
+    if rowbias is not None:
+        ref = ref + rowbias.float()[torch.arange(M, device=dev) // rpb]
+    if resid is not None:
+        ref = ref + resid.float()
+    assert rel_rms(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("force", [SINGLE, PAIR, 0])
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,stride,flags,lora", [
+    (1, 32, 32, 64, 0, 64, 1, "", None),
+    (1, 64, 64, 320, 0, 320, 1, "bt", None),       # conv1 of a ResnetBlock2D: + time-embedding row bias
+    (1, 128, 128, 320, 0, 320, 1, "bR", None),     # conv2: + residual, one image row per tile
+    (2, 32, 32, 1280, 640, 1280, 1, "b", None),    # skip-connection concat as two sources
+    (2, 64, 64, 320, 0, 320, 2, "b", None),        # Downsample2D (stride 2, parity planes)
+    (2, 32, 32, 640, 0, 640, 1, "bL", (4, 0.5)),   # LoRA conv: down 3x3 folded in, up 1x1 in the epilogue
+    (3, 8, 8, 128, 0, 128, 1, "b", None),          # 8x8 level: tiles span images, ragged M
+    (1, 16, 16, 128, 64, 64, 1, "b", None),
+])
+def test_conv3x3(dev, force, B, H, W, C0, C1, Cout, stride, flags, lora):
+    from sliders_b200 import ops
+
+    g = torch.Generator().manual_seed(B * H + C0 + Cout)
+    Cin = C0 + C1
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev, BF)
+    w = (torch.randn(Cout, 3, 3, Cin, generator=g) / (9 * Cin) ** 0.5).to(dev, BF)
+    Ho, Wo = H // stride, W // stride
+    bias = torch.randn(Cout, generator=g).to(dev, BF) if "b" in flags else None
+    rowbias = torch.randn(B, Cout, generator=g).to(dev, BF) if "t" in flags else None
+    resid = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev, BF) if "R" in flags else None
+    la = None
+    if lora:
+        r, scale = lora
+        down, up, rt = make_lora(9 * Cin, Cout, r, Cout, dev, 9)
+        la = ops.Lora(down, up, r, Cout, scale)
+    x0 = x[..., :C0].contiguous()
+    x1 = x[..., C0:].contiguous() if C1 else None
+    out = ops.conv3x3(x0, w, x1=x1, stride=stride, bias=bias, rowbias=rowbias, resid=resid, lora=la, bn=force)
+    torch.cuda.synchronize()
+    xn = x.float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xn, w.float().permute(0, 3, 1, 2), None, stride=stride, padding=1)
+    if lora:
+        dn = down.float().view(-1, 3, 3, Cin).permute(0, 3, 1, 2)
+        t = F.conv2d(xn, dn, None, stride=stride, padding=1)
+        ref = ref + torch.einsum("brhw,or->bohw", t[:, :r], up) * scale
+    ref = ref.permute(0, 2, 3, 1)
+    if bias is not None:
+        ref = ref + bias.float()
+    if rowbias is not None:
+        ref = ref + rowbias.float()[:, None, None, :]
+    if resid is not None:
+        ref = ref + resid.float()
+    assert rel_rms(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,heads,Sq,Skv,fused", [
+    (1, 1, 128, 128, False), (2, 5, 1024, 1024, True), (2, 4, 1024, 77, False),  # cross-attention: 77 keys
+    (1, 2, 64, 64, True),      # Sq, Skv below one tile
+    (1, 3, 320, 200, False),   # ragged queries and keys
+    (1, 10, 4096, 4096, True),  # SDXL 64x64 level
+])
+def test_attention(dev, B, heads, Sq, Skv, fused):
+    from sliders_b200 import ops
+
+    g = torch.Generator().manual_seed(Sq + Skv)
+    Cc = heads * 64
+    if fused:
+        qkv = torch.randn(B * Sq, 3 * Cc, generator=g).to(dev, BF)
+        q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+    else:
+        q = torch.randn(B * Sq, Cc, generator=g).to(dev, BF)
+        kv = torch.randn(B * Skv, 2 * Cc, generator=g).to(dev, BF)
+        k, v = kv[:, :Cc], kv[:, Cc:]
+    out = ops.attention(q, k, v, B, heads, Sq, Skv, 0.125)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, Sq, heads, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Skv, heads, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Skv, heads, 64).transpose(1, 2)
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, dim=-1) @ vf).transpose(1, 2).reshape(B * Sq, Cc)
+    assert rel_rms(out, ref) < 2e-2
+
+
+def test_attention_softmax_rows_sum_to_one(dev):
+    """Size-independent property: with V = 1 the output is exactly the row sum of P / l = 1."""
+    from sliders_b200 import ops
+
+    B, heads, S = 2, 4, 1024
+    g = torch.Generator().manual_seed(0)
+    q = (torch.randn(B * S, heads * 64, generator=g) * 3).to(dev, BF)
+    k = (torch.randn(B * S, heads * 64, generator=g) * 3).to(dev, BF)
+    v = torch.ones(B * S, heads * 64, device=dev, dtype=BF)
+    out = ops.attention(q, k, v, B, heads, S, S, 0.125)
+    assert (out.float() - 1).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,HW,C0,C1,silu,eps", [(2, 1024, 320, 0, True, 1e-5), (2, 4096, 640, 320, True, 1e-5),
+                                                (1, 16384, 320, 0, False, 1e-6), (3, 64, 64, 64, True, 1e-5),
+                                                (2, 256, 1280, 640, True, 1e-5)])  # 1920/32 = 60: groups straddle
+def test_groupnorm(dev, B, HW, C0, C1, silu, eps):
+    from sliders_b200 import ops
+
+    g = torch.Generator().manual_seed(HW + C0)
+    Cc = C0 + C1
+    x = (torch.randn(B, HW, Cc, generator=g) * 2 + 0.5).to(dev, BF)
+    gamma = (1 + 0.1 * torch.randn(Cc, generator=g)).to(dev, BF)
+    beta = (0.1 * torch.randn(Cc, generator=g)).to(dev, BF)
+    x0 = x[..., :C0].contiguous()
+    x1 = x[..., C0:].contiguous() if C1 else None
+    out = ops.groupnorm(x0, gamma, beta, 32, eps, silu, x1=x1)
+    out2 = ops.groupnorm(x0, gamma, beta, 32, eps, silu, x1=x1)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().transpose(1, 2), 32, gamma.float(), beta.float(), eps).transpose(1, 2)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_rms(out, ref) < 1e-2
+    assert torch.equal(out, out2)  # atomic-free reduction: bit-reproducible
+
+
+@pytest.mark.parametrize("M,Cc", [(2048, 640), (1000, 1280), (77, 128), (33, 320)])
+def test_layernorm(dev, M, Cc):
+    from sliders_b200 import ops
+
+    g = torch.Generator().manual_seed(M)
+    x = (torch.randn(M, Cc, generator=g) * 3 - 1).to(dev, BF)
+    gamma = (1 + 0.1 * torch.randn(Cc, generator=g)).to(dev, BF)
+    beta = (0.1 * torch.randn(Cc, generator=g)).to(dev, BF)
+    out = ops.layernorm(x, gamma, beta, 1e-5)
+    ref = F.layer_norm(x.float(), (Cc,), gamma.float(), beta.float(), 1e-5)
+    assert rel_rms(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,act_in,act_out,lora,resid", [
+    (2, 1280, 320, False, 1, None, False), (8, 1280, 2816, False, 1, None, False),
+    (4, 640, 1280, True, 0, None, False), (16, 320, 1280, False, 0, (4, 0.5), False),
+    (3, 1280, 1280, True, 0, (8, -1.5), False), (2, 1280, 1280, False, 2, None, True),
+])
+def test_small_linear(dev, M, N, K, act_in, act_out, lora, resid):
+    from sliders_b200 import ops
+
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(dev, BF)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev, BF)
+    b = torch.randn(N, generator=g).to(dev, BF)
+    res = torch.randn(M, N, generator=g).to(dev, BF) if resid else None
+    la = None
+    if lora:
+        r, scale = lora
+        down, up, rt = make_lora(K, N, r, N, dev, 5)
+        la = ops.Lora(down, up, r, N, scale)
+    out = ops.small_linear(x, w, b, act_in=act_in, act_out=act_out, lora=la, resid=res)
+    xin = F.silu(x.float()).to(BF).float() if act_in else x.float()
+    ref = xin @ w.float().t() + b.float()
+    if lora:
+        ref = ref + (xin @ down.float()[:r].t()) @ up.t() * scale
+    if act_out == 1:
+        ref = F.silu(ref)
+    if res is not None:
+        ref = ref + res.float()
+    if act_out == 2:
+        ref = F.silu(ref.to(BF).float())
+    assert rel_rms(out, ref) < 1e-2
+
+
+def test_sinusoid_conv_in_out_upsample_cfg_ddim(dev):
+    from sliders_b200 import ops
+
+    vals = torch.tensor([0.0, 1.0, 500.0, 999.0, 1024.0], device=dev)
+    out = ops.sinusoid(vals, 320)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(160, device=dev, dtype=torch.float32) / 160)
+    arg = vals[:, None] * freqs[None]
+    assert rel_rms(out, torch.cat([torch.cos(arg), torch.sin(arg)], -1)) < 5e-3
+    g = torch.Generator().manual_seed(1)
+    lat = torch.randn(2, 4, 32, 32, generator=g).to(dev)
+    w = (torch.randn(320, 3, 3, 4, generator=g) / 6).to(dev, BF)
+    b = torch.randn(320, generator=g).to(dev, BF)
+    ref = F.conv2d(lat.to(BF).float(), w.float().permute(0, 3, 1, 2), b.float(), padding=1).permute(0, 2, 3, 1)
+    assert rel_rms(ops.conv_in(lat, w, b), ref) < 1e-2
+    assert rel_rms(ops.conv_in(lat.to(BF), w, b), ref) < 1e-2
+    x = torch.randn(2, 32, 32, 320, generator=g).to(dev, BF)
+    w = (torch.randn(4, 3, 3, 320, generator=g) / 54).to(dev, BF)
+    b = torch.randn(4, generator=g).to(dev, BF)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b.float(), padding=1)
+    assert rel_rms(ops.conv_out(x, w, b, out_dtype=torch.float32), ref) < 1e-5
+    assert rel_rms(ops.conv_out(x, w, b), ref) < 1e-2
+    x = torch.randn(2, 8, 8, 64, generator=g).to(dev, BF)
+    assert torch.equal(ops.upsample2x(x), x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    n = 2 * 4 * 32 * 32
+    eps2 = torch.randn(2, 2, 4, 32, 32, generator=g).reshape(4, 4, 32, 32).to(dev, BF)
+    xx = torch.randn(2, 4, 32, 32, generator=g).to(dev)
+    e, xp = ops.cfg_ddim(eps2, 3.0, xx, 0.3, 0.5)
+    eu, ec = eps2[:2].float(), eps2[2:].float()
+    er = eu + 3.0 * (ec - eu)
+    assert rel_rms(e, er) < 1e-6
+    x0 = (xx - (1 - 0.3) ** 0.5 * er) / 0.3 ** 0.5
+    assert rel_rms(xp, 0.5 ** 0.5 * x0 + 0.5 ** 0.5 * er) < 1e-6
+    # idempotence-style property: guidance 1 returns the conditional half (train_util.py:250-253)
+    e1, _ = ops.cfg_ddim(eps2, 1.0)
+    assert torch.allclose(e1.float(), ec, atol=1e-2)
+
+
+def test_bad_arguments_return_errors_not_crashes(dev):
+    from sliders_b200 import _cabi, ops
+
+    x = torch.zeros(128, 60, device=dev, dtype=BF)  # K = 60 is not a multiple of 8
+    w = torch.zeros(64, 60, device=dev, dtype=BF)
+    with pytest.raises(_cabi.Sb200Error, match="multiples of 8"):
+        ops.gemm(x, w)
+    with pytest.raises(_cabi.Sb200Error, match="must divide 128"):
+        ops.conv3x3(torch.zeros(1, 96, 96, 64, device=dev, dtype=BF), torch.zeros(64, 3, 3, 64, device=dev, dtype=BF))
+    with pytest.raises(_cabi.Sb200Error, match="CUDA tensors"):
+        ops.layernorm(torch.zeros(4, 64, dtype=BF), torch.zeros(64, dtype=BF), torch.zeros(64, dtype=BF))

@@ -1,0 +1,225 @@
+"""GPU parity tests of the whole hot path: sliders_b200.UNet2DConditionModel + LoRANetwork + train_util
+(`predict_noise(_xl)`, `diffusion_xl`) through the C ABI versus (a) the committed golden vectors that the
+reference's own unmodified lora.py / train_util.py produced on the oracle (tests/golden/make_golden.py) and (b) the
+fp32 oracle run live on the same seeded weights / inputs.
+
+Tolerance (BASELINE.json north_star: "within a stated fp16 tolerance"): the kernels compute in bf16 with fp32
+accumulation, the oracle in fp32.  Stated bound: relative RMS error of the predicted noise <= 2.5e-2 for a single
+conditioned pass and for guidance-combined eps (guidance g multiplies the difference of two passes, so the bound is
+looser for g = 7.5: 6e-2); max-abs error <= 0.15 on eps ~ N(0, 0.6).  For context, PyTorch's own bf16 autocast of
+the oracle differs from the fp32 oracle by 0.9e-2 rel-RMS on the full SDXL UNet (profiles/r01_unet_sdxl.log), our
+kernels by 0.75e-2."""
+import os
+
+import pytest
+import torch
+
+from conftest import c3lier
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def rel_rms(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert torch.isfinite(got).all()
+    return ((got - ref).norm() / ref.norm()).item()
+
+
+def build_product(fx, dev):
+    """Product UNet + LoRANetwork with the fixture's seeded weights (regenerated, not stored)."""
+    from oracle import unet as ounet
+    from sliders_b200 import lora as plora, synthetic
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    ocfg = getattr(ounet.UNetConfig, fx["config"])()
+    pm = UNet2DConditionModel(UNetConfig.from_dict(ocfg.__dict__))
+    synthetic.init_synthetic_(pm, seed=fx["weight_seed"])  # CPU generator: identical to the oracle's weights
+    pm = pm.to(dev, BF).eval()
+    pm.requires_grad_(False)
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=fx["rank"], multiplier=1.0, alpha=fx["alpha"], train_method="noxattn")
+    synthetic.init_lora_nonzero_(net, seed=fx["lora_seed"], up_std=fx["up_std"], reseed_down=True)
+    net = net.to(dev, BF)
+    assert len(net.unet_loras) == fx["n_lora"]
+    return pm, net
+
+
+def test_golden_tiny_xl_reference_call_sites(dev):
+    """predict_noise_xl / diffusion_xl / set_lora_slider semantics against what the reference's code produced."""
+    from sliders_b200 import train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+
+    fx = torch.load(os.path.join(GOLDEN, "tiny_xl.pt"))
+    pm, net = build_product(fx, dev)
+    sched = create_noise_scheduler("ddim")
+    lat, ehs = fx["latents"].to(dev), fx["text_embeddings"].to(dev)
+    pooled, tids = fx["add_text_embeddings"].to(dev), fx["add_time_ids"].to(dev)
+    t = fx["timestep"]
+    sched.set_timesteps(1000)
+    assert int(sched.timesteps[500]) == t
+    with torch.no_grad():
+        net.__exit__(None, None, None)  # multiplier 0 outside the context manager (lora.py:256-258)
+        off1 = train_util.predict_noise_xl(pm, sched, t, lat, ehs, pooled, tids, guidance_scale=1)
+        off3 = train_util.predict_noise_xl(pm, sched, t, lat, ehs, pooled, tids, guidance_scale=3)
+        with net:
+            on1 = train_util.predict_noise_xl(pm, sched, t, lat, ehs, pooled, tids, guidance_scale=1)
+        net.set_lora_slider(-2.0)
+        with net:
+            onm2 = train_util.predict_noise_xl(pm, sched, t, lat, ehs, pooled, tids, guidance_scale=3)
+        net.set_lora_slider(1.0)
+        sched.set_timesteps(50)
+        with net:
+            den = train_util.diffusion_xl(pm, sched, lat, ehs, pooled, tids, guidance_scale=3, total_timesteps=3)
+    assert rel_rms(off1, fx["eps_off_g1"]) < 2.5e-2
+    assert rel_rms(off3, fx["eps_off_g3"]) < 2.5e-2
+    assert rel_rms(on1, fx["eps_on_s1_g1"]) < 2.5e-2
+    assert rel_rms(onm2, fx["eps_on_sm2_g3"]) < 2.5e-2
+    assert rel_rms(den, fx["denoised_3of50_g3"]) < 2.5e-2
+    assert (off1.float().cpu() - fx["eps_off_g1"]).abs().max() < 0.15
+    # the adaptor's effect is resolved well above the error floor, with the right sign for a negative slider
+    eff = fx["eps_on_s1_g1"] - fx["eps_off_g1"]
+    got_eff = (on1 - off1).float().cpu()
+    assert torch.nn.functional.cosine_similarity(got_eff.flatten(), eff.flatten(), dim=0) > 0.98
+    # loss formula on the four predictions (prompt_util.py:123-135), enhance, guidance 4
+    loss = torch.nn.functional.mse_loss(on1.float(), off1.float() + 4.0 * (off3.float() - onm2.float()))
+    assert abs(loss.item() - fx["loss_enhance_g4"].item()) / fx["loss_enhance_g4"].item() < 5e-2
+
+
+def test_golden_tiny_sd_predict_noise(dev):
+    """SD1.x topology (conv projections, 4 levels, no text_time embedding), rank 8, alpha 4, batch 2."""
+    from sliders_b200 import train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+
+    fx = torch.load(os.path.join(GOLDEN, "tiny_sd.pt"))
+    pm, net = build_product(fx, dev)
+    sched = create_noise_scheduler("ddim")
+    sched.set_timesteps(1000)
+    lat, ehs, t = fx["latents"].to(dev), fx["text_embeddings"].to(dev), fx["timestep"]
+    with torch.no_grad():
+        net.__exit__(None, None, None)
+        off = train_util.predict_noise(pm, sched, t, lat, ehs, guidance_scale=7.5)
+        with net:
+            on = train_util.predict_noise(pm, sched, t, lat, ehs, guidance_scale=1)
+    assert rel_rms(off, fx["eps_off_g7.5"]) < 6e-2  # guidance 7.5 amplifies the difference of two bf16 passes
+    assert rel_rms(on, fx["eps_on_s1_g1"]) < 2.5e-2
+
+
+def test_identities_bit_exact(dev):
+    """Zero-initialised LoRA == no LoRA; multiplier 0 == no LoRA; CUDA-graph replay == eager; run-to-run
+    reproducibility — all bit-exact (no atomics anywhere on the path)."""
+    from sliders_b200 import lora as plora, synthetic
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+    from oracle import unet as ounet
+
+    ocfg = ounet.UNetConfig.tiny_xl()
+    with torch.device(dev):
+        pm = UNet2DConditionModel(UNetConfig.from_dict(ocfg.__dict__)).to(BF)
+    synthetic.init_synthetic_(pm, seed=3)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 32, 32, generator=g).to(dev)
+    ehs = torch.randn(2, 77, 256, generator=g).to(dev, BF)
+    added = {"text_embeds": torch.randn(2, 128, generator=g).to(dev, BF),
+             "time_ids": torch.tensor([[256., 256, 0, 0, 256, 256]] * 2, device=dev)}
+    with torch.no_grad():
+        base = pm(x, 321, ehs, added_cond_kwargs=added).sample
+        again = pm(x, 321, ehs, added_cond_kwargs=added).sample
+        assert torch.equal(base, again)
+        with c3lier(plora):
+            net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+        with net:
+            fresh = pm(x, 321, ehs, added_cond_kwargs=added).sample  # lora_up == 0
+        assert torch.equal(fresh, base)
+        synthetic.init_lora_nonzero_(net, seed=4, up_std=0.05)
+        off = pm(x, 321, ehs, added_cond_kwargs=added).sample  # multiplier 0 after __exit__
+        assert torch.equal(off, base)
+        net.set_lora_slider(1.5)
+        with net:
+            on = pm(x, 321, ehs, added_cond_kwargs=added).sample
+        assert not torch.equal(on, base)
+        pm.use_cuda_graph = True
+        with net:
+            g_on = pm(x, 321, ehs, added_cond_kwargs=added).sample
+        net.set_lora_slider(-0.5)
+        with net:
+            g_neg = pm(x, 321, ehs, added_cond_kwargs=added).sample  # same graph, slider read from device memory
+        g_off = pm(x, 321, ehs, added_cond_kwargs=added).sample
+        pm.use_cuda_graph = False
+        with net:
+            e_neg = pm(x, 321, ehs, added_cond_kwargs=added).sample
+        assert torch.equal(g_on, on) and torch.equal(g_neg, e_neg) and torch.equal(g_off, base)
+        # linearity in the slider value for small scales is a property of the folded epilogue: eps(s) - eps(0)
+        # changes sign with s
+        d_pos, d_neg = (on - base).float(), (e_neg - base).float()
+        assert torch.nn.functional.cosine_similarity(d_pos.flatten(), d_neg.flatten(), dim=0) < -0.5
+
+
+def test_grad_request_fails_loudly(dev):
+    from sliders_b200 import lora as plora
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+    from oracle import unet as ounet
+
+    with torch.device(dev):
+        pm = UNet2DConditionModel(UNetConfig.from_dict(ounet.UNetConfig.tiny_xl().__dict__)).to(BF)
+    pm.requires_grad_(False)
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+    x = torch.zeros(1, 4, 32, 32, device=dev)
+    with net, pytest.raises(NotImplementedError, match="forward"):
+        pm(x, 1, torch.zeros(1, 77, 256, device=dev, dtype=BF),
+           added_cond_kwargs={"text_embeds": torch.zeros(1, 128, device=dev), "time_ids": torch.zeros(1, 6, device=dev)})
+
+
+@pytest.mark.parametrize("batch", [2])
+def test_full_sdxl_parity_vs_fp32_oracle(dev, batch):
+    """BASELINE workload size: SDXL-base UNet (2.57 B parameters, synthetic seeded weights), 128x128 latents, rank-4
+    LoRA on 346 leaves at slider 2.  The oracle runs in fp32 on the same device (plain PyTorch, TF32 off) with the
+    LoRA delta folded into its weights; tests/test_oracle.py pins that folding to the reference's forward hook."""
+    from oracle import unet as ounet
+    from sliders_b200 import lora as plora, synthetic
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    with torch.device(dev):
+        pm = UNet2DConditionModel(UNetConfig.sdxl()).to(BF)
+        om = ounet.UNet2DConditionModel(ounet.UNetConfig.sdxl())
+    synthetic.init_synthetic_(pm, seed=1)
+    om.load_state_dict({k: v.float() for k, v in pm.state_dict().items()})
+    om.eval()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 4, 128, 128, generator=g).to(dev, BF)
+    ehs = torch.randn(batch, 77, 2048, generator=g).to(dev, BF)
+    added = {"text_embeds": torch.randn(batch, 1280, generator=g).to(dev, BF),
+             "time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * batch, device=dev)}
+    addf = {"text_embeds": added["text_embeds"].float(), "time_ids": added["time_ids"]}
+    with torch.no_grad():
+        got = pm(x, 500, ehs, added_cond_kwargs=added).sample
+        ref = om(x.float(), 500, ehs.float(), added_cond_kwargs=addf).sample
+    assert rel_rms(got, ref) < 2.5e-2
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+    assert len(net.unet_loras) == 346
+    synthetic.init_lora_nonzero_(net, seed=2, up_std=0.05)
+    mods = {("lora_unet_" + n.replace(".", "_")): m for n, m in om.named_modules()}
+    sd = net.state_dict()
+    with torch.no_grad():
+        for l in net.unet_loras:
+            up, down = sd[l.lora_name + ".lora_up.weight"].float(), sd[l.lora_name + ".lora_down.weight"].float()
+            delta = torch.einsum("or,rikl->oikl", up[:, :, 0, 0], down) if down.dim() == 4 else up @ down
+            mods[l.lora_name].weight.add_(delta * (2.0 * l.scale))
+        ref_l = om(x.float(), 19, ehs.float(), added_cond_kwargs=addf).sample
+        net.set_lora_slider(2.0)
+        with net:
+            got_l = pm(x, 19, ehs, added_cond_kwargs=added).sample
+    assert rel_rms(got_l, ref_l) < 2.5e-2
+    assert (got_l.float() - ref_l).abs().max().item() < 0.15

@@ -1,0 +1,209 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every declared symbol, the product
+module tree / LoRANetwork mirror the reference interface, the product DDIM scheduler agrees with the oracle
+restatement, checkpoints round-trip in the reference layout, and the multi-rank fan-out helpers reproduce the
+single-rank result under gloo with world_size 2.  No GPU compute happens here."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import c3lier
+from oracle import ddim as oddim
+from oracle import reference_bridge as rb
+from sliders_b200 import _cabi, lora as plora, parallel, scheduler as psched, synthetic
+from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------- C ABI
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+
+    if not os.path.exists(_cabi.lib_path()):
+        ge.build()
+    lib = _cabi.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/sb200.h but not exported"
+        assert name in _cabi.SIGNATURES, f"{name} has no ctypes prototype in _cabi.SIGNATURES"
+    assert lib.sb200_version().decode() == "sb200 0.1 sm_100a"
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    """`tcgen05.mma` shows up as UTC*MMA, TMA as UTMALDG, tcgen05.ld as LDTM (B200_PROFILING.md)."""
+    if not os.path.exists(_cabi.lib_path()):
+        pytest.skip("library not built")
+    sass = subprocess.run(["cuobjdump", "-sass", _cabi.lib_path()], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass
+    assert "UTMALDG" in sass
+    assert "LDTM" in sass and "STTM" in sass
+    assert "HMMA.16816" not in sass  # no legacy mma.sync path
+
+
+def test_no_cpu_fallback():
+    m = UNet2DConditionModel(UNetConfig.from_dict(dict(block_out_channels=(64, 128), down_block_types=(
+        "DownBlock2D", "CrossAttnDownBlock2D"), up_block_types=("CrossAttnUpBlock2D", "UpBlock2D"),
+        transformer_layers_per_block=(1, 1), attention_head_dim=(1, 2), cross_attention_dim=64)))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 4, 8, 8), 10, encoder_hidden_states=torch.zeros(1, 77, 64))
+    with pytest.raises(RuntimeError, match="parameter container"):
+        m.mid_block(torch.zeros(1))
+
+
+# ---------------------------------------------------------------------------------------- module tree / LoRA API
+@pytest.mark.parametrize("cfg,n_leaves,n_params", [(UNetConfig.sdxl(), 346, 4_320_000), (UNetConfig.sd15(), 150, 2_906_880)])
+def test_product_lora_counts(cfg, n_leaves, n_params):
+    with torch.device("meta"):
+        m = UNet2DConditionModel(cfg)
+        with c3lier(plora):
+            net = plora.LoRANetwork(m, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn")
+    assert len(net.unet_loras) == n_leaves
+    assert sum(p.numel() for p in net.parameters()) == n_params
+    # without c3lier only the Attention leaves (lierla)
+    with torch.device("meta"):
+        m = UNet2DConditionModel(cfg)
+        net2 = plora.LoRANetwork(m, rank=4, alpha=1.0, train_method="noxattn")
+    assert len(net2.unet_loras) == (280 if n_leaves == 346 else 64)
+
+
+def test_lora_module_semantics():
+    with torch.device("meta"):
+        m = UNet2DConditionModel(UNetConfig.sd15())
+    with c3lier(plora):
+        net = plora.LoRANetwork(m, rank=8, multiplier=1.0, alpha=4.0, train_method="full")
+    l = net.unet_loras[0]
+    assert l.scale == 4.0 / 8 and l.lora_dim == 8 and float(l.alpha) == 4.0
+    assert set(k.split(".", 1)[1] for k in net.state_dict() if k.startswith(l.lora_name + ".")) == {
+        "alpha", "lora_down.weight", "lora_up.weight"}
+    # context-manager semantics (lora.py:249-258)
+    assert all(x.multiplier == 1.0 for x in net.unet_loras)  # constructor value before the first exit
+    net.set_lora_slider(-3.0)
+    with net:
+        assert all(x.multiplier == -3.0 for x in net.unet_loras)
+    assert all(x.multiplier == 0 for x in net.unet_loras)
+    # the leaf's forward is swapped for the adaptor's bound method: how the engine discovers adaptors
+    from sliders_b200.unet import _adaptor_of
+
+    leaf = m.down_blocks[0].attentions[0].transformer_blocks[0].attn1.to_q
+    assert _adaptor_of(leaf) is getattr(net, "lora_unet_down_blocks_0_attentions_0_transformer_blocks_0_attn1_to_q")
+    with pytest.raises(RuntimeError, match="no eager path"):
+        leaf.forward(torch.zeros(1))
+    groups = net.prepare_optimizer_params()
+    assert len(groups) == 1 and len(groups[0]["params"]) == 2 * len(net.unet_loras)
+    conv = [x for x in net.unet_loras if x.lora_name.endswith("resnets_0_conv1")][0]
+    assert conv.lora_down.weight.shape[2:] == (3, 3) and conv.lora_up.weight.shape[2:] == (1, 1)
+
+
+def test_checkpoint_roundtrip_pt_and_safetensors(tmp_path):
+    cfg = UNetConfig.from_dict(dict(block_out_channels=(64, 128), down_block_types=("DownBlock2D", "CrossAttnDownBlock2D"),
+                                    up_block_types=("CrossAttnUpBlock2D", "UpBlock2D"),
+                                    transformer_layers_per_block=(1, 1), attention_head_dim=(1, 2), cross_attention_dim=64))
+    m = UNet2DConditionModel(cfg)
+    with c3lier(plora):
+        net = plora.LoRANetwork(m, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn")
+    synthetic.init_lora_nonzero_(net, seed=3)
+    for ext in (".pt", ".safetensors"):
+        f = str(tmp_path / f"slider_alpha1.0_rank4_noxattn_last{ext}")
+        net.save_weights(f, dtype=torch.bfloat16)
+        if ext == ".pt":
+            sd = torch.load(f)
+        else:
+            from safetensors.torch import load_file
+
+            sd = load_file(f)
+        assert all(v.dtype == torch.bfloat16 for v in sd.values())
+        m2 = UNet2DConditionModel(cfg)
+        with c3lier(plora):
+            net2 = plora.LoRANetwork(m2, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn")
+        missing = net2.load_state_dict(sd, strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        for k, v in net.state_dict().items():
+            assert torch.equal(net2.state_dict()[k].to(torch.bfloat16), v.to(torch.bfloat16)), k
+    if rb.available():  # a slider written by us loads into the reference's own LoRANetwork on the oracle UNet
+        from oracle import unet as ounet
+
+        rlora = rb.load("lora")
+        om = ounet.UNet2DConditionModel(ounet.UNetConfig(**cfg.__dict__))
+        with c3lier(rlora):
+            rnet = rlora.LoRANetwork(om, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn")
+        rnet.load_state_dict(torch.load(str(tmp_path / "slider_alpha1.0_rank4_noxattn_last.pt")), strict=True)
+
+
+# ---------------------------------------------------------------------------------------- scheduler
+def test_product_ddim_matches_oracle_ddim():
+    a = psched.create_noise_scheduler("ddim")
+    b = oddim.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                            num_train_timesteps=1000, clip_sample=False)
+    assert torch.equal(a.alphas_cumprod, b.alphas_cumprod)
+    for n in (50, 1000, 30):
+        a.set_timesteps(n)
+        b.set_timesteps(n)
+        assert torch.equal(a.timesteps, b.timesteps)
+    a.set_timesteps(50)
+    b.set_timesteps(50)
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    for t in (980, 500, 0):
+        assert torch.allclose(a.step(e, t, x).prev_sample, b.step(e, t, x).prev_sample, atol=1e-6)
+    ts = torch.tensor([300])
+    assert torch.allclose(a.add_noise(x, e, ts), b.add_noise(x, e, ts))
+    assert a.init_noise_sigma == 1.0 and a.scale_model_input(x, 3) is x
+    with pytest.raises(NotImplementedError):
+        psched.create_noise_scheduler("euler_a")
+
+
+# ---------------------------------------------------------------------------------------- multi-rank fan-out (gloo)
+def test_shard_range_partitions():
+    for n in (1, 3, 8, 11):
+        for w in (1, 2, 4, 8):
+            spans = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sliders_b200 import parallel
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+g = torch.Generator().manual_seed(0)
+lat = torch.randn(5, 4, 8, 8, generator=g); emb = torch.randn(5, 7, 16, generator=g)
+W = torch.randn(16, 4, generator=g)
+def predict(l, e, scale=1.0):   # stand-in for the UNet: any per-pass-independent function
+    return torch.tanh(l * scale) + (e.mean(1) @ W)[:, :, None, None]
+full = predict(lat, emb, scale=0.5)
+got = parallel.fanout_predict(predict, (lat, emb), scale=0.5)
+assert torch.equal(got, full), "fan-out result differs from the single-rank result"
+p = torch.nn.Parameter(torch.ones(6)); q = torch.nn.Parameter(torch.ones(2, 3))
+if dist.get_rank() == 0:
+    p.grad = torch.arange(6.0); q.grad = None          # rank 1 holds no graph for q... and rank 0 none for q
+else:
+    p.grad = torch.ones(6); q.grad = torch.full((2, 3), 2.0)
+parallel.allreduce_lora_grads([p, q])
+assert torch.equal(p.grad, torch.arange(6.0) + 1) and torch.equal(q.grad, torch.full((2, 3), 2.0))
+dist.destroy_process_group()
+print("ok")
+'''
+
+
+def test_fanout_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29500 + (os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o

@@ -28,6 +28,7 @@ dev = torch.device("cuda:0")
 h = C.c_void_p()
 assert lib.sb200_create(0, C.byref(h)) == 0, lib.sb200_last_error()
 results = []
+FORCE = 0  # 0 auto, 0x2000 single-CTA kernel, 0x1000 CTA-pair (cta_group::2) kernel
 
 
 def stream():
@@ -61,7 +62,7 @@ def lora_args(K, N, r, rt, group_n, scale, seed):
     down[: groups * r] = torch.randn(groups * r, K, generator=g) / K ** 0.5
     up = torch.randn(N, r, generator=g) * 0.5
     down = down.to(dev, torch.bfloat16)
-    up = up.to(dev, torch.bfloat16)
+    up = up.to(torch.bfloat16).float().to(dev)  # sb200_lora.up is fp32 (bf16-representable values)
     la = _cabi.LoraArgs(down.data_ptr(), up.data_ptr(), r, rt, group_n, scale)
     return la, down, up
 
@@ -99,7 +100,7 @@ def run_gemm(M, N, K, flags=0, split=0, lora=None, bn=0, seed=0, name=None):
     else:
         a0, l0, a1, l1, k0 = x, K, None, 0, K
     st = lib.sb200_gemm(h, stream(), ptr(a0), l0, ptr(a1), l1, k0, ptr(w), K, ptr(out), nout, M, N, K, flags,
-                        ptr(bias), ptr(rowbias), rpb, ptr(resid), nout, C.byref(la) if la else None, bn)
+                        ptr(bias), ptr(rowbias), rpb, ptr(resid), nout, C.byref(la) if la else None, bn | FORCE)
     chk(st)
     torch.cuda.synchronize()
     ref = x.float() @ w.float().t()
@@ -115,7 +116,7 @@ def run_gemm(M, N, K, flags=0, split=0, lora=None, bn=0, seed=0, name=None):
         ref = ref + rowbias.float()[idx]
     if flags & _cabi.EPI_RESID:
         ref = ref + resid.float()
-    return report(name or f"gemm M{M} N{N} K{K} flags{flags} split{split} lora{lora} bn{bn}", out, ref)
+    return report((name or f"gemm M{M} N{N} K{K} flags{flags} split{split} lora{lora} bn{bn}") + f" force{FORCE:#x}", out, ref)
 
 
 def run_conv(B, H, W, C0, C1, Cout, stride=1, flags=0, lora=None, bn=0, seed=0):
@@ -136,7 +137,7 @@ def run_conv(B, H, W, C0, C1, Cout, stride=1, flags=0, lora=None, bn=0, seed=0):
         la, down, up = lora_args(9 * Cin, Cout, r, rt, group_n, scale, seed + 1)
     st = lib.sb200_conv3x3(h, stream(), ptr(x0), C0, ptr(x1), C1, C0, C1, ptr(w), ptr(out), Cout, B, H, W, Cout,
                            stride, flags, ptr(bias), ptr(rowbias), ptr(resid), Cout,
-                           C.byref(la) if la else None, bn)
+                           C.byref(la) if la else None, bn | FORCE)
     chk(st)
     torch.cuda.synchronize()
     xn = x.float().permute(0, 3, 1, 2)
@@ -154,7 +155,7 @@ def run_conv(B, H, W, C0, C1, Cout, stride=1, flags=0, lora=None, bn=0, seed=0):
         ref = ref + rowbias.float()[:, None, None, :]
     if flags & _cabi.EPI_RESID:
         ref = ref + resid.float()
-    return report(f"conv B{B} {H}x{W} C{C0}+{C1}->{Cout} s{stride} flags{flags} lora{lora} bn{bn}", out, ref)
+    return report(f"conv B{B} {H}x{W} C{C0}+{C1}->{Cout} s{stride} flags{flags} lora{lora} bn{bn} force{FORCE:#x}", out, ref)
 
 
 def bench_gemm(M, N, K, flags=0, bn=0, iters=20):
@@ -163,8 +164,9 @@ def bench_gemm(M, N, K, flags=0, bn=0, iters=20):
     nout = N // 2 if flags & _cabi.EPI_GEGLU else N
     out = torch.empty(M, nout, device=dev, dtype=torch.bfloat16)
     bias = torch.zeros(N, device=dev, dtype=torch.bfloat16)
+    resid = torch.randn(M, nout, device=dev).to(torch.bfloat16) if flags & _cabi.EPI_RESID else None
     args = (h, stream(), ptr(x), K, None, 0, K, ptr(w), K, ptr(out), nout, M, N, K, flags, ptr(bias), None, 1,
-            None, 0, None, bn)
+            ptr(resid), nout, None, bn | FORCE)
     for _ in range(3):
         chk(lib.sb200_gemm(*args))
     torch.cuda.synchronize()
@@ -186,7 +188,7 @@ def bench_gemm(M, N, K, flags=0, bn=0, iters=20):
     e1.record()
     torch.cuda.synchronize()
     ms_t = e0.elapsed_time(e1) / iters
-    print(f"PERF gemm M{M} N{N} K{K} flags{flags} bn{bn}: {ms * 1e3:.1f} us {tf:.0f} TFLOP/s | cuBLAS "
+    print(f"PERF gemm M{M} N{N} K{K} flags{flags} bn{bn} force{FORCE:#x}: {ms * 1e3:.1f} us {tf:.0f} TFLOP/s | cuBLAS "
           f"{ms_t * 1e3:.1f} us {2.0 * M * N * K / ms_t / 1e9:.0f} TFLOP/s", flush=True)
     results.append({"name": f"perf M{M} N{N} K{K} f{flags} bn{bn}", "us": ms * 1e3, "tflops": tf,
                     "cublas_us": ms_t * 1e3})
@@ -197,30 +199,35 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     B_, R_, RB_, G_, L_ = _cabi.EPI_BIAS, _cabi.EPI_RESID, _cabi.EPI_ROWBIAS, _cabi.EPI_GEGLU, _cabi.EPI_LORA
     ok = True
-    # 1. smallest possible: one tile, one k-block
-    ok &= run_gemm(128, 64, 64, bn=64, name="gemm 1 tile 1 kblock")
-    ok &= run_gemm(128, 128, 256, bn=128, name="gemm 1 tile 4 kblocks")
-    ok &= run_gemm(256, 256, 512, bn=128)
-    ok &= run_gemm(1024, 1280, 1280, flags=B_)
-    ok &= run_gemm(1000, 640, 640, flags=B_ | R_)             # M tail
-    ok &= run_gemm(77 * 2, 1280, 2048)                        # cross-attn K/V shape
-    ok &= run_gemm(2048, 2560, 640, flags=B_ | G_)            # GEGLU
-    ok &= run_gemm(1024, 640, 1920, flags=B_, split=1280)     # concat shortcut
-    ok &= run_gemm(1024, 1280, 1280, flags=B_ | L_, lora=(4, 16, 1280, 0.25))
-    ok &= run_gemm(1024, 1920, 640, flags=L_, lora=(4, 16, 640, 1.0))  # fused qkv
-    ok &= run_gemm(512, 640, 640, flags=L_ | B_ | R_, lora=(8, 16, 640, -2.0))
-    ok &= run_gemm(4096, 1280, 1280, flags=B_ | RB_ | R_)
-    if which in ("all", "conv"):
-        ok &= run_conv(1, 32, 32, 64, 0, 64, bn=64)
-        ok &= run_conv(2, 32, 32, 128, 0, 128, flags=B_)
-        ok &= run_conv(1, 64, 64, 320, 0, 320, flags=B_ | RB_)
-        ok &= run_conv(1, 128, 128, 320, 0, 320, flags=B_ | R_)
-        ok &= run_conv(2, 32, 32, 1280, 640, 1280, flags=B_)  # concat
-        ok &= run_conv(2, 64, 64, 320, 0, 320, stride=2, flags=B_)
-        ok &= run_conv(2, 32, 32, 640, 0, 640, flags=B_ | L_, lora=(4, 16, 640, 0.5))
-        ok &= run_conv(3, 8, 8, 128, 0, 128, flags=B_)       # SD1.x smallest level (bb=2, M tail)
-        ok &= run_conv(1, 16, 16, 128, 64, 64, flags=B_)
+    for FORCE in ((0x2000, 0x1000, 0) if which != 'pair' else (0x1000,)):
+        globals()['FORCE'] = FORCE
+        print(f'---- force {FORCE:#x}', flush=True)
+        # 1. smallest possible: one tile, one k-block
+        ok &= run_gemm(128, 64, 64, bn=64, name="gemm 1 tile 1 kblock")
+        ok &= run_gemm(128, 128, 256, bn=128, name="gemm 1 tile 4 kblocks")
+        ok &= run_gemm(256, 256, 512, bn=128)
+        ok &= run_gemm(1024, 1280, 1280, flags=B_)
+        ok &= run_gemm(1000, 640, 640, flags=B_ | R_)             # M tail
+        ok &= run_gemm(77 * 2, 1280, 2048)                        # cross-attn K/V shape
+        ok &= run_gemm(2048, 2560, 640, flags=B_ | G_)            # GEGLU
+        ok &= run_gemm(1024, 640, 1920, flags=B_, split=1280)     # concat shortcut
+        ok &= run_gemm(1024, 1280, 1280, flags=B_ | L_, lora=(4, 16, 1280, 0.25))
+        ok &= run_gemm(1024, 1920, 640, flags=L_, lora=(4, 16, 640, 1.0))  # fused qkv
+        ok &= run_gemm(512, 640, 640, flags=L_ | B_ | R_, lora=(8, 16, 640, -2.0))
+        ok &= run_gemm(4096, 1280, 1280, flags=B_ | RB_ | R_)
+        if which in ("all", "conv"):
+            ok &= run_conv(1, 32, 32, 64, 0, 64, bn=64)
+            ok &= run_conv(2, 32, 32, 128, 0, 128, flags=B_)
+            ok &= run_conv(1, 64, 64, 320, 0, 320, flags=B_ | RB_)
+            ok &= run_conv(1, 128, 128, 320, 0, 320, flags=B_ | R_)
+            ok &= run_conv(2, 32, 32, 1280, 640, 1280, flags=B_)  # concat
+            ok &= run_conv(2, 64, 64, 320, 0, 320, stride=2, flags=B_)
+            ok &= run_conv(2, 32, 32, 640, 0, 640, flags=B_ | L_, lora=(4, 16, 640, 0.5))
+            ok &= run_conv(3, 8, 8, 128, 0, 128, flags=B_)       # SD1.x smallest level (bb=2, M tail)
+            ok &= run_conv(1, 16, 16, 128, 64, 64, flags=B_)
     if which in ("all", "perf"):
+      for FORCE in (0x2000, 0x1000, 0):
+        globals()['FORCE'] = FORCE
         bench_gemm(8192, 1280, 1280)
         bench_gemm(8192, 10240, 1280, flags=G_ | B_)
         bench_gemm(8192, 1280, 5120, flags=B_)
@@ -228,6 +235,8 @@ if __name__ == "__main__":
         bench_gemm(32768, 640, 640)
         bench_gemm(8192, 8192, 8192)
         bench_gemm(8192, 8192, 8192, bn=128)
+        bench_gemm(8192, 1280, 1280, flags=B_ | R_)
+        bench_gemm(32768, 640, 640, flags=B_ | R_)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/gemm_check.json", "w") as f:
         json.dump(results, f, indent=1)

@@ -127,7 +127,7 @@ def small_linear_case(M, N, K, act_in, act_out, lora=None, seed=0):
         down = torch.zeros(16, K)
         down[:r] = torch.randn(r, K, generator=g) / K ** 0.5
         up = torch.randn(N, r, generator=g) * 0.5
-        down, up = down.to(dev, BF), up.to(dev, BF)
+        down, up = down.to(dev, BF), up.to(BF).float().to(dev)  # up is fp32 in the ABI
         la = _cabi.LoraArgs(down.data_ptr(), up.data_ptr(), r, 16, N, scale)
     _cabi.check(lib.sb200_small_linear(h, stream(), ptr(x), K, ptr(w), K, ptr(b), ptr(out), N, M, N, K, act_in,
                                        act_out, C.byref(la) if la else None, None))
