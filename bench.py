@@ -43,6 +43,33 @@ UNIT = "passes/s"
 LATENT = 128
 
 
+def host_threads() -> int:
+    """CPU threads this process can really use: min(affinity mask, cgroup CPU quota).  os.cpu_count() alone
+    reports the host's cores (128 on the GPU boxes) even when the container is throttled to a fraction of them, and
+    oversubscribing a quota makes the fp32 oracle several times slower."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts and parts[0] != "max":
+                    n = min(n, max(1, int(float(parts[0]) / float(parts[1]) + 0.5)))
+            else:
+                quota = int(parts[0])
+                with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                    period = int(f2.read().split()[0])
+                if quota > 0:
+                    n = min(n, max(1, int(quota / period + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    env = os.environ.get("SLIDERS_CPU_THREADS")
+    if env:
+        n = int(env)
+    return max(1, min(n, 64))  # MKL/oneDNN fp32 convs stop scaling (and start thrashing) well before 64 threads
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -208,7 +235,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         from sliders_b200 import synthetic
         from oracle import unet as ounet
         with torch.device("meta"):
@@ -366,7 +393,7 @@ def main():
     # ---- CPU baseline (rank 0, N == 1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         sd = {k: v.detach().float().cpu() for k, v in unet.state_dict().items()}
         nsd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
         scales = {l.lora_name: float(l.scale) for l in net.unet_loras}

@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         mbar_wait(bar_vfull + 8 * s, ph);
         mbar_wait(bar_pfull, j & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        const int kv_left = p.Skv - j * 128;
+        const int ksteps = kv_left >= 128 ? 8 : (kv_left + 15) >> 4;  // keys beyond Skv contribute nothing
+        for (int k = 0; k < ksteps; ++k) {
           umma_ts(tmem_base + kColO, tmem_base + kColP + k * 8,
                   umma_desc_sw128(sV + s * kTileBytes + k * 2048), idesc_pv, (j | k) != 0);
         }

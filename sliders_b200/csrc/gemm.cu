@@ -63,6 +63,7 @@ struct GemmParams {
   int cb_total;     // k-blocks per tap
   int H, W;         // conv OUTPUT spatial dims
   int flags;
+  int debug;        // profiling experiments only: bit 0 skip W loads, bit 1 skip A loads (results are garbage)
   const __nv_bfloat16* bias;
   const __nv_bfloat16* rowbias;
   int rows_per_batch;
@@ -198,7 +199,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             full = mapa_u32(full, 0);
             if (leader) mbar_expect_tx(bar_full + 8u * stage, static_cast<uint32_t>(p.stage_bytes) * 2u);
           } else {
-            mbar_expect_tx(full, static_cast<uint32_t>(p.stage_bytes));
+            mbar_expect_tx(full, static_cast<uint32_t>(p.stage_bytes) - ((p.debug & 1) ? b_bytes : 0u) -
+                                     ((p.debug & 2) ? a_bytes : 0u));
           }
           const uint32_t sA = tiles + static_cast<uint32_t>(stage) * p.stage_bytes;
           const uint32_t sB = sA + a_bytes;
@@ -240,12 +242,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             tma_load_2d_2cta(sB, &p.tmB, full, kb * kBK, brow);
             if (has_lora) tma_load_2d_2cta(sB + b_bytes, &p.tmL, full, kb * kBK, static_cast<int>(cta_rank) * p.l_rows);
           } else {
-            if (p.a_mode == 0)
-              tma_load_2d(sA, amap, full, c0, c1);
-            else
-              tma_load_4d(sA, amap, full, c0, c1, c2, c3);
-            tma_load_2d(sB, &p.tmB, full, kb * kBK, brow);
-            if (geglu)
+            if (!(p.debug & 2)) {
+              if (p.a_mode == 0)
+                tma_load_2d(sA, amap, full, c0, c1);
+              else
+                tma_load_4d(sA, amap, full, c0, c1, c2, c3);
+            }
+            if (!(p.debug & 1)) tma_load_2d(sB, &p.tmB, full, kb * kBK, brow);
+            if (geglu && !(p.debug & 1))
               tma_load_2d(sB + static_cast<uint32_t>(p.bn >> 1) * 128, &p.tmB, full, kb * kBK,
                           (p.N >> 1) + nt * (p.bn >> 1));
             if (has_lora) tma_load_2d(sB + b_bytes, &p.tmL, full, kb * kBK, 0);
@@ -588,7 +592,8 @@ static int check_lora(const sb200_lora* l, int N) {
 
 // bn encodes an explicit choice when > 0: low 12 bits = tile width, bit 12 set = force the CTA-pair kernel,
 // bit 13 set = force the single-CTA kernel (used by the tests to cover both).
-static void decode_bn(int bn_arg, int* bn, int* force_ctas) {
+static void decode_bn(int bn_arg, int* bn, int* force_ctas, int* debug = nullptr) {
+  if (debug) *debug = bn_arg > 0 ? (bn_arg >> 14) & 3 : 0;
   *force_ctas = (bn_arg > 0 && (bn_arg & 0x1000)) ? 2 : ((bn_arg > 0 && (bn_arg & 0x2000)) ? 1 : 0);
   *bn = bn_arg > 0 ? (bn_arg & 0xFFF) : 0;
 }
@@ -645,7 +650,7 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
   }
   const int step = geglu ? 32 : 16;
   int bn, force_ctas;
-  decode_bn(bn_arg, &bn, &force_ctas);
+  decode_bn(bn_arg, &bn, &force_ctas, &p.debug);
   TileChoice tc = pick_tile(M, N, max_bn, step, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, pair_allowed(), force_ctas);
   if (bn > 0) tc.bn = bn;
   if (force_ctas) tc.ctas = force_ctas;

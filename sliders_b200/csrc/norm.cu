@@ -80,21 +80,29 @@ __global__ void gn_stats_kernel(GnArgs a, float* __restrict__ partial) {
   }
 }
 
-// final[b][g] = {mean, rstd}
+// final[b][g] = {mean, rstd}; one warp per group, fixed-order lane-strided sum + shuffle tree (deterministic)
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ final_stats,
                                    int chunks, int groups, float inv_n, float eps) {
   const int b = blockIdx.x;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (int g = threadIdx.x >> 5; g < groups; g += blockDim.x >> 5) {
     float S = 0.f, SS = 0.f;
-    for (int k = 0; k < chunks; ++k) {
-      const float* pp = partial + ((static_cast<size_t>(b) * chunks + k) * groups + g) * 2;
-      S += pp[0];
-      SS += pp[1];
+    for (int k = lane; k < chunks; k += 32) {
+      const float2 pp = *reinterpret_cast<const float2*>(partial + ((static_cast<size_t>(b) * chunks + k) * groups + g) * 2);
+      S += pp.x;
+      SS += pp.y;
     }
-    const float mean = S * inv_n;
-    const float var = fmaxf(SS * inv_n - mean * mean, 0.f);
-    final_stats[(static_cast<size_t>(b) * groups + g) * 2] = mean;
-    final_stats[(static_cast<size_t>(b) * groups + g) * 2 + 1] = rsqrtf(var + eps);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      S += __shfl_xor_sync(0xffffffffu, S, o);
+      SS += __shfl_xor_sync(0xffffffffu, SS, o);
+    }
+    if (lane == 0) {
+      const float mean = S * inv_n;
+      const float var = fmaxf(SS * inv_n - mean * mean, 0.f);
+      final_stats[(static_cast<size_t>(b) * groups + g) * 2] = mean;
+      final_stats[(static_cast<size_t>(b) * groups + g) * 2 + 1] = rsqrtf(var + eps);
+    }
   }
 }
 
@@ -109,51 +117,55 @@ struct GnApplyArgs {
   int silu;
 };
 
+// grid (chunks, B), block = (C/8) * rows_par threads like gn_stats_kernel: a thread owns one 8-channel vector,
+// folds (mean, rstd, gamma, beta) into scale/shift once and then streams its rows: 16 B in, 8 FMA (+SiLU), 16 B out.
 __global__ void gn_apply_kernel(GnApplyArgs a, const float* __restrict__ stats) {
   const GnArgs& in = a.in;
   const int nvec = in.C >> 3;
-  const size_t total = static_cast<size_t>(a.B) * in.HW * nvec;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(idx % nvec);
-    const size_t pix = idx / nvec;  // b * HW + r
-    const int b = static_cast<int>(pix / in.HW);
-    const int c = cv << 3;
-    const __nv_bfloat16* src;
-    int ld, cc;
-    if (c < in.C0) {
-      src = in.x0, ld = in.ld0, cc = c;
-    } else {
-      src = in.x1, ld = in.ld1, cc = c - in.C0;
-    }
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + pix * ld + cc));
+  const int cv = threadIdx.x % nvec;
+  const int r0 = threadIdx.x / nvec;
+  const int rows_par = blockDim.x / nvec;
+  const int b = blockIdx.y;
+  const int c = cv << 3;
+  const __nv_bfloat16* src;
+  int ld, cc;
+  if (c < in.C0) {
+    src = in.x0, ld = in.ld0, cc = c;
+  } else {
+    src = in.x1, ld = in.ld1, cc = c - in.C0;
+  }
+  float sc[8], sh[8];
+  {
     const uint4 gv = __ldg(reinterpret_cast<const uint4*>(a.gamma + c));
     const uint4 bv = __ldg(reinterpret_cast<const uint4*>(a.beta + c));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
     const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-    float f[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f[2 * i] = bf16_lo(w[i]);
-      f[2 * i + 1] = bf16_hi(w[i]);
-    }
     const float* st = stats + static_cast<size_t>(b) * 2 * in.groups;
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int g = (c + i) / in.cpg;
-      if (g != g_prev) {
-        g_prev = g;
-        mean = st[2 * g];
-        rstd = st[2 * g + 1];
-      }
+      const float mean = st[2 * g], rstd = st[2 * g + 1];
       const float gm = (i & 1) ? bf16_hi(gw[i >> 1]) : bf16_lo(gw[i >> 1]);
       const float bt = (i & 1) ? bf16_hi(bw[i >> 1]) : bf16_lo(bw[i >> 1]);
-      float y = (f[i] - mean) * rstd * gm + bt;
-      if (a.silu) y = silu_f(y);
-      f[i] = y;
+      sc[i] = rstd * gm;
+      sh[i] = bt - mean * rstd * gm;
+    }
+  }
+  const int row_begin = blockIdx.x * in.rows_per_block;
+  const int row_end = min(row_begin + in.rows_per_block, in.HW);
+  for (int r = row_begin + r0; r < row_end; r += rows_par) {
+    const size_t pix = static_cast<size_t>(b) * in.HW + r;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + pix * ld + cc));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = fmaf(bf16_lo(w[i]), sc[2 * i], sh[2 * i]);
+      f[2 * i + 1] = fmaf(bf16_hi(w[i]), sc[2 * i + 1], sh[2 * i + 1]);
+    }
+    if (a.silu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
     }
     uint4 o;
     o.x = pack_bf16x2(f[0], f[1]);
@@ -169,6 +181,7 @@ __global__ void gn_apply_kernel(GnApplyArgs a, const float* __restrict__ stats) 
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnMaxVec = 8;  // C <= 8 * 32 * 8 = 2048
 
+template <int NV>  // 16-byte vectors per lane: C <= NV * 256
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                  const __nv_bfloat16* __restrict__ gamma,
                                  const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out,
@@ -179,10 +192,10 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
        row += gridDim.x * warps_per_block) {
     const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ldx;
-    float f[kLnMaxVec][8];
+    float f[NV][8];
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < nvec) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
@@ -200,7 +213,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
     const float mean = sum / C;
     float var = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       if (lane + k * 32 < nvec) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -214,7 +227,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
     const float rstd = rsqrtf(var / C + eps);
     __nv_bfloat16* orow = out + static_cast<size_t>(row) * ldo;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < nvec) {
         const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + v * 8));
@@ -277,7 +290,7 @@ extern "C" int sb200_groupnorm(void* handle, void* stream, const void* x0, int l
   float* final_stats = stats_ws + static_cast<size_t>(B) * kGnMaxChunks * groups * 2;
   gn_stats_kernel<<<dim3(chunks, B), threads, sizeof(float) * 2 * C * rows_par, s>>>(a, stats_ws);
   SB200_CUDA_CHECK(cudaGetLastError());
-  gn_finalize_kernel<<<B, 64, 0, s>>>(stats_ws, final_stats, chunks, groups,
+  gn_finalize_kernel<<<B, 1024, 0, s>>>(stats_ws, final_stats, chunks, groups,
                                       1.f / (static_cast<float>(HW) * a.cpg), eps);
   SB200_CUDA_CHECK(cudaGetLastError());
   GnApplyArgs ap;
@@ -289,11 +302,7 @@ extern "C" int sb200_groupnorm(void* handle, void* stream, const void* x0, int l
   ap.B = B;
   ap.eps = eps;
   ap.silu = silu;
-  const size_t total = static_cast<size_t>(B) * HW * nvec;
-  int blocks = static_cast<int>((total + 255) / 256);
-  const int max_blocks = ctx->num_sms * 16;
-  if (blocks > max_blocks) blocks = max_blocks;
-  gn_apply_kernel<<<blocks, 256, 0, s>>>(ap, final_stats);
+  gn_apply_kernel<<<dim3(chunks, B), threads, 0, s>>>(ap, final_stats);
   SB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -306,11 +315,23 @@ extern "C" int sb200_layernorm(void* handle, void* stream, const void* x, int ld
   SB200_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0, "layernorm: leading dims");
   const int warps = 8;
   int blocks = (M + warps - 1) / warps;
-  const int max_blocks = ctx->num_sms * 8;
+  const int max_blocks = ctx->num_sms * 16;
   if (blocks > max_blocks) blocks = max_blocks;
-  layernorm_kernel<<<blocks, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(gamma),
-      static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(out), ldo, M, C, eps);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define SB200_LN(NV)                                                                                      \
+  layernorm_kernel<NV><<<blocks, warps * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx,            \
+                                                      static_cast<const __nv_bfloat16*>(gamma),             \
+                                                      static_cast<const __nv_bfloat16*>(beta),              \
+                                                      static_cast<__nv_bfloat16*>(out), ldo, M, C, eps)
+  if (C <= 256)
+    SB200_LN(1);
+  else if (C <= 768)
+    SB200_LN(3);
+  else if (C <= 1280)
+    SB200_LN(5);
+  else
+    SB200_LN(8);
+#undef SB200_LN
   SB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

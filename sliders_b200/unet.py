@@ -448,7 +448,37 @@ class UNet2DConditionModel(nn.Module):
             self._packed[key] = v
         return v
 
-    def _attn(self, attn: Attention, x_norm, resid, B, S, ctx=None, Sctx=0):
+    # ---- cross-attention K/V for every transformer block in one GEMM per channel width ----------------------
+    def _kv_plan(self):
+        """attn2.to_k|to_v of all blocks with the same width stacked into one [n_blocks*2C, Dctx] matrix: the 70
+        per-block [77*B, 2048] x [2C, 2048]^T projections of SDXL share their input (encoder_hidden_states), so they
+        run as 2 well-shaped GEMMs instead of 70 launches with 5 row tiles each."""
+        plan = self._packed.get("kvplan")
+        if plan is None:
+            groups: Dict[int, list] = {}
+            for m in self.modules():
+                if isinstance(m, Attention) and m.is_cross:
+                    groups.setdefault(m.to_k.weight.shape[0], []).append(m)
+            plan = {}
+            for C_, mods in groups.items():
+                w = torch.cat([torch.cat([a.to_k.weight.detach(), a.to_v.weight.detach()], 0).to(BF16) for a in mods], 0)
+                plan[C_] = (w.contiguous(), {id(a): i * 2 * C_ for i, a in enumerate(mods)}, mods)
+            self._packed["kvplan"] = plan
+        return plan
+
+    def _cross_kv(self, ctx):
+        """{C: (kv_all [B*77, n_blocks*2C], offsets)} or None when an active adaptor sits on a to_k / to_v of attn2
+        (train methods xattn / full: those keep the per-block fused path with its own LoRA stack)."""
+        plan = self._kv_plan()
+        for _, _, mods in plan.values():
+            for a in mods:
+                for leaf in (a.to_k, a.to_v):
+                    ad = _adaptor_of(leaf)
+                    if ad is not None and float(ad.multiplier) * float(ad.scale) != 0.0:
+                        return None
+        return {C_: (ops.gemm(ctx, w), offs) for C_, (w, offs, _) in plan.items()}
+
+    def _attn(self, attn: Attention, x_norm, resid, B, S, ctx=None, Sctx=0, kv_all=None):
         """x_norm: [B*S, C] normalised input; returns resid + to_out(attention)."""
         C_ = attn.to_q.weight.shape[0]
         if attn.dim_head != 64:
@@ -461,13 +491,19 @@ class UNet2DConditionModel(nn.Module):
             o = ops.attention(qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:], B, attn.heads, S, S, scale)
         else:
             q = ops.gemm(x_norm, self._w(attn.to_q), lora=self._lora([attn.to_q]))
-            kvl = [attn.to_k, attn.to_v]
-            kv = ops.gemm(ctx, self._fused_w(kvl), lora=self._lora(kvl))
-            o = ops.attention(q, kv[:, :C_], kv[:, C_:], B, attn.heads, S, Sctx, scale)
+            if kv_all is not None:
+                kv, offs = kv_all[C_]
+                off = offs[id(attn)]
+                k, v = kv[:, off:off + C_], kv[:, off + C_:off + 2 * C_]
+            else:
+                kvl = [attn.to_k, attn.to_v]
+                kv = ops.gemm(ctx, self._fused_w(kvl), lora=self._lora(kvl))
+                k, v = kv[:, :C_], kv[:, C_:]
+            o = ops.attention(q, k, v, B, attn.heads, S, Sctx, scale)
         out = attn.to_out[0]
         return ops.gemm(o, self._w(out), bias=self._b(out), resid=resid, lora=self._lora([out]))
 
-    def _transformer(self, tr: Transformer2DModel, x, ctx, Sctx) -> torch.Tensor:
+    def _transformer(self, tr: Transformer2DModel, x, ctx, Sctx, kv_all=None) -> torch.Tensor:
         B, H, W, C_ = x.shape
         S = H * W
         res = x.view(B * S, C_)
@@ -478,7 +514,7 @@ class UNet2DConditionModel(nn.Module):
             n = ops.layernorm(h, *self._w_norm(blk.norm1), eps=blk.norm1.eps)
             h = self._attn(blk.attn1, n, h, B, S)
             n = ops.layernorm(h, *self._w_norm(blk.norm2), eps=blk.norm2.eps)
-            h = self._attn(blk.attn2, n, h, B, S, ctx=ctx, Sctx=Sctx)
+            h = self._attn(blk.attn2, n, h, B, S, ctx=ctx, Sctx=Sctx, kv_all=kv_all)
             n = ops.layernorm(h, *self._w_norm(blk.norm3), eps=blk.norm3.eps)
             ffp, ffo = blk.ff.net[0].proj, blk.ff.net[2]
             f = ops.gemm(n, self._w(ffp), bias=self._b(ffp), geglu=True)
@@ -510,6 +546,7 @@ class UNet2DConditionModel(nn.Module):
         B = sample.shape[0]
         Sctx = ehs.shape[1]
         ctx = ehs.reshape(B * Sctx, ehs.shape[-1])
+        kv_all = self._cross_kv(ctx)
         emb = self._embeddings(timesteps_f32, B, added_cond_kwargs)
         h = ops.conv_in(sample, self._w(self.conv_in), self._b(self.conv_in))
         skips = [h]
@@ -518,7 +555,7 @@ class UNet2DConditionModel(nn.Module):
             for i, rn in enumerate(blk.resnets):
                 h = self._resnet(rn, h, None, emb)
                 if attns is not None:
-                    h = self._transformer(attns[i], h, ctx, Sctx)
+                    h = self._transformer(attns[i], h, ctx, Sctx, kv_all)
                 skips.append(h)
             if blk.downsamplers is not None:
                 conv = blk.downsamplers[0].conv
@@ -526,14 +563,14 @@ class UNet2DConditionModel(nn.Module):
                 skips.append(h)
         mid = self.mid_block
         h = self._resnet(mid.resnets[0], h, None, emb)
-        h = self._transformer(mid.attentions[0], h, ctx, Sctx)
+        h = self._transformer(mid.attentions[0], h, ctx, Sctx, kv_all)
         h = self._resnet(mid.resnets[1], h, None, emb)
         for blk in self.up_blocks:
             attns = getattr(blk, "attentions", None)
             for i, rn in enumerate(blk.resnets):
                 h = self._resnet(rn, h, skips.pop(), emb)
                 if attns is not None:
-                    h = self._transformer(attns[i], h, ctx, Sctx)
+                    h = self._transformer(attns[i], h, ctx, Sctx, kv_all)
             if blk.upsamplers is not None:
                 conv = blk.upsamplers[0].conv
                 h = ops.upsample2x(h)
