@@ -95,32 +95,41 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   const int n = p.n_kv_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // converged warp, one ELECTed lane issues (a `lane == 0` branch makes ptxas wrap every uniform-datapath
+    // instruction in an ELECT / BRA.U.ANY retry loop)
+    if (elect_one()) {
       mbar_expect_tx(bar_q, kTileBytes);
       tma_load_3d(sQ, &p.tmQ, bar_q, head * 64, qt * 128, b);
-      for (int j = 0; j < n; ++j) {
-        const int s = j % kAttnStages;
-        const uint32_t ph = (j / kAttnStages) & 1;
-        mbar_wait(bar_kempty + 8 * s, ph ^ 1u);
+    }
+    __syncwarp();
+    for (int j = 0; j < n; ++j) {
+      const int s = j % kAttnStages;
+      const uint32_t ph = (j / kAttnStages) & 1;
+      mbar_wait(bar_kempty + 8 * s, ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(bar_kfull + 8 * s, kTileBytes);
         tma_load_3d(sK + s * kTileBytes, &p.tmK, bar_kfull + 8 * s, head * 64, j * 128, b);
-        mbar_wait(bar_vempty + 8 * s, ph ^ 1u);
+      }
+      __syncwarp();
+      mbar_wait(bar_vempty + 8 * s, ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(bar_vfull + 8 * s, kTileBytes);
         tma_load_3d(sV + s * kTileBytes, &p.tmV, bar_vfull + 8 * s, head * 64, j * 128, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
-      const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);  // B (= V) is MN-major
-      mbar_wait(bar_q, 0);
-      for (int j = 0; j < n; ++j) {
-        const int s = j % kAttnStages;
-        const uint32_t ph = (j / kAttnStages) & 1;
-        // ---- S_j = Q K_j^T
-        mbar_wait(bar_kfull + 8 * s, ph);
-        mbar_wait(bar_sfree, (j & 1) ^ 1u);  // softmax finished reading S_{j-1}
-        tc_fence_after();
+    const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);  // B (= V) is MN-major
+    mbar_wait(bar_q, 0);
+    for (int j = 0; j < n; ++j) {
+      const int s = j % kAttnStages;
+      const uint32_t ph = (j / kAttnStages) & 1;
+      // ---- S_j = Q K_j^T
+      mbar_wait(bar_kfull + 8 * s, ph);
+      mbar_wait(bar_sfree, (j & 1) ^ 1u);  // softmax finished reading S_{j-1}
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           umma_ss(tmem_base + kColS, umma_desc_sw128(sQ + k * 32),
@@ -128,10 +137,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         }
         umma_commit(bar_kempty + 8 * s);
         umma_commit(bar_sfull);
-        // ---- O += P_j V_j
-        mbar_wait(bar_vfull + 8 * s, ph);
-        mbar_wait(bar_pfull, j & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      // ---- O += P_j V_j
+      mbar_wait(bar_vfull + 8 * s, ph);
+      mbar_wait(bar_pfull, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const int kv_left = p.Skv - j * 128;
         const int ksteps = kv_left >= 128 ? 8 : (kv_left + 15) >> 4;  // keys beyond Skv contribute nothing
         for (int k = 0; k < ksteps; ++k) {
@@ -141,6 +153,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         umma_commit(bar_vempty + 8 * s);
         umma_commit(bar_pvdone);
       }
+      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- softmax / correction / store
@@ -212,14 +225,24 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
           if (lane == 0) mbar_arrive(bar_sfree);
         }
         uint32_t pk[16];
+        if (kv_left >= (c + 1) * 32) {  // warp-uniform: no masking code on full chunks
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_run));
-          float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_run));
-          if (c * 32 + 2 * i >= kv_left) p0 = 0.f;
-          if (c * 32 + 2 * i + 1 >= kv_left) p1 = 0.f;
-          lsum += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_run));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_run));
+            lsum += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_run));
+            float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_run));
+            if (c * 32 + 2 * i >= kv_left) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= kv_left) p1 = 0.f;
+            lsum += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
         }
         tmem_st_x16(tl + kColP + c * 16, pk);
       }

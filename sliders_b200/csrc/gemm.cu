@@ -39,6 +39,7 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarRegion = 1024;
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // UMMA smem descriptor, high word
 constexpr int kSlab = 32;             // output columns staged per epilogue-warp iteration
 constexpr int kEpiBufBytes = 32 * 64; // [32 rows x 32 cols] bf16
 constexpr int kEpiBytesPerWarp = 2 * kEpiBufBytes;
@@ -102,7 +103,9 @@ __device__ __forceinline__ void lora_apply(float* f, const float* t, const float
   }
 }
 
-template <int kCtas>
+// kElect: producer / MMA roles run as converged warps whose ELECTed lane issues (clean SASS) instead of a
+// `lane == 0` branch (ptxas then wraps each uniform-datapath instruction in an ELECT / BRA.U.ANY retry loop).
+template <int kCtas, bool kElect>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -165,7 +168,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (every CTA)
-    if (lane == 0) {
+    // One lane runs the whole role.  (A converged warp with an ELECTed issuer gives cleaner SASS — no ELECT /
+    // BRA.U.ANY retry loop around every UTMALDG / UTCHMMA — but measured 12-15 % slower on B200, see
+    // profiles/r01_gemm_experiments.md, so the single-lane form stays.)
+    if (kElect || lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = unit; t < total_tiles; t += num_units) {
@@ -188,8 +194,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         } else {
           brow = nt * p.bn + static_cast<int>(cta_rank) * p.b_rows;
         }
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+        for (int kb = 0; kb < ((p.debug & 4) ? 0 : p.kblocks); ++kb) {
+          if (!kElect || lane == 0) mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+          if (kElect) __syncwarp();
+          if (!kElect || elect_one()) {
           uint32_t full = bar_full + 8u * stage;
           if constexpr (kCtas == 2) {
             // Both CTAs' TMA bytes are counted on the LEADER's barrier; only the leader arrives (expecting the
@@ -197,7 +205,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             // stage completed (its empty barrier is released by the leader's commit after that phase), and a
             // transiently negative tx-count inside the right phase is legal.
             full = mapa_u32(full, 0);
-            if (leader) mbar_expect_tx(bar_full + 8u * stage, static_cast<uint32_t>(p.stage_bytes) * 2u);
+            if (leader)
+              mbar_expect_tx(bar_full + 8u * stage, 2u * (static_cast<uint32_t>(p.stage_bytes) - ((p.debug & 1) ? b_bytes : 0u) -
+                                                          ((p.debug & 2) ? a_bytes : 0u)));
           } else {
             mbar_expect_tx(full, static_cast<uint32_t>(p.stage_bytes) - ((p.debug & 1) ? b_bytes : 0u) -
                                      ((p.debug & 2) ? a_bytes : 0u));
@@ -235,11 +245,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             c3 = b0;
           }
           if constexpr (kCtas == 2) {
-            if (p.a_mode == 0)
-              tma_load_2d_2cta(sA, amap, full, c0, c1);
-            else
-              tma_load_4d_2cta(sA, amap, full, c0, c1, c2, c3);
-            tma_load_2d_2cta(sB, &p.tmB, full, kb * kBK, brow);
+            if (!(p.debug & 2)) {
+              if (p.a_mode == 0)
+                tma_load_2d_2cta(sA, amap, full, c0, c1);
+              else
+                tma_load_4d_2cta(sA, amap, full, c0, c1, c2, c3);
+            }
+            if (!(p.debug & 1)) tma_load_2d_2cta(sB, &p.tmB, full, kb * kBK, brow);
             if (has_lora) tma_load_2d_2cta(sB + b_bytes, &p.tmL, full, kb * kBK, static_cast<int>(cta_rank) * p.l_rows);
           } else {
             if (!(p.debug & 2)) {
@@ -254,6 +266,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
                           (p.N >> 1) + nt * (p.bn >> 1));
             if (has_lora) tma_load_2d(sB + b_bytes, &p.tmL, full, kb * kBK, 0);
           }
+          }
+          if (kElect) __syncwarp();
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    if ((kElect || lane == 0) && leader) {
       const uint32_t idesc = umma_idesc_bf16(kBM * kCtas, p.bn);
       const uint32_t idesc_l = umma_idesc_bf16(kBM * kCtas, has_lora ? p.lora_rt : 16);
       int stage = 0;
@@ -271,38 +285,47 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       int as = 0;
       uint32_t aphase = 0;
       for (int t = unit; t < total_tiles; t += num_units) {
-        mbar_wait(bar_tempty + 8u * as, aphase ^ 1u);
+        if (!kElect || lane == 0) mbar_wait(bar_tempty + 8u * as, aphase ^ 1u);
+        if (kElect) __syncwarp();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
         for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(bar_full + 8u * stage, phase);
+          if ((!kElect || lane == 0) && !(p.debug & 4)) mbar_wait(bar_full + 8u * stage, phase);
+          if (kElect) __syncwarp();
           tc_fence_after();
-          const uint32_t sA = tiles + static_cast<uint32_t>(stage) * p.stage_bytes;
-          const uint32_t sB = sA + a_bytes;
-          const uint32_t sL = sB + b_bytes;
+          if (!kElect || elect_one()) {
+            const uint32_t sA = tiles + static_cast<uint32_t>(stage) * p.stage_bytes;
+            const uint32_t sB = sA + a_bytes;
+            const uint32_t sL = sB + b_bytes;
+            // descriptor = {hi: SBO 1024 B | version 1 | SWIZZLE_128B, lo: (address >> 4)}; +2 per 16-element k-step
+            const uint32_t a_lo = (sA & 0x3FFFF) >> 4, b_lo = (sB & 0x3FFFF) >> 4, l_lo = (sL & 0x3FFFF) >> 4;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t adesc = umma_desc_sw128(sA + k * 32);
-            const uint64_t bdesc = umma_desc_sw128(sB + k * 32);
-            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2u * k);
+              const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2u * k);
+              const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+              if constexpr (kCtas == 2) {
+                umma_ss_2cta(d_tmem, adesc, bdesc, idesc, acc);
+                if (has_lora)
+                  umma_ss_2cta(d_tmem + static_cast<uint32_t>(p.bn), adesc,
+                               (static_cast<uint64_t>(kDescHi) << 32) | (l_lo + 2u * k), idesc_l, acc);
+              } else {
+                umma_ss((p.debug & 16) ? (d_tmem ^ ((k & 1) ? 256u : 0u)) : d_tmem, adesc, bdesc, idesc, acc);  // debug 16: alternate accumulators
+                if (has_lora)
+                  umma_ss(d_tmem + static_cast<uint32_t>(p.bn), adesc,
+                          (static_cast<uint64_t>(kDescHi) << 32) | (l_lo + 2u * k), idesc_l, acc);
+              }
+            }
+            // free the smem stage (in every CTA of the pair) once these MMAs retire
             if constexpr (kCtas == 2) {
-              umma_ss_2cta(d_tmem, adesc, bdesc, idesc, acc);
-              if (has_lora)
-                umma_ss_2cta(d_tmem + static_cast<uint32_t>(p.bn), adesc, umma_desc_sw128(sL + k * 32), idesc_l, acc);
+              umma_commit_2cta(bar_empty + 8u * stage, 3);
+              if (kb == p.kblocks - 1) umma_commit_2cta(bar_tfull + 8u * as, 3);
             } else {
-              umma_ss(d_tmem, adesc, bdesc, idesc, acc);
-              if (has_lora)
-                umma_ss(d_tmem + static_cast<uint32_t>(p.bn), adesc, umma_desc_sw128(sL + k * 32), idesc_l, acc);
+              if (!(p.debug & 4)) umma_commit(bar_empty + 8u * stage);
+              if (kb == p.kblocks - 1) umma_commit(bar_tfull + 8u * as);
             }
           }
-          // free the smem stage (in every CTA of the pair) once these MMAs retire
-          if constexpr (kCtas == 2) {
-            umma_commit_2cta(bar_empty + 8u * stage, 3);
-            if (kb == p.kblocks - 1) umma_commit_2cta(bar_tfull + 8u * as, 3);
-          } else {
-            umma_commit(bar_empty + 8u * stage);
-            if (kb == p.kblocks - 1) umma_commit(bar_tfull + 8u * as);
-          }
+          if (kElect) __syncwarp();
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -336,7 +359,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       const int n_base = nt * p.ncols_out;
       const int ncols_valid = min(p.ncols_out, p.Nout - n_base);
       const int nslabs = (ncols_valid + kSlab - 1) / kSlab;
-      const int my_slabs = (nslabs - hsel + 1) >> 1;  // slabs hsel, hsel+2, ...
+      const int my_slabs = (p.debug & 8) ? 0 : ((nslabs - hsel + 1) >> 1);  // slabs hsel, hsel+2, ... (debug 8: skip)
       auto prefetch_resid = [&](int col0, int sw, uint32_t buf) {
         const int cpr = sw >> 3;  // 16-byte chunks per row
         for (int idx = lane; idx < 32 * cpr; idx += 32) {
@@ -539,7 +562,16 @@ static bool pair_allowed() {
   return v;
 }
 
+static bool elect_issue_default() {
+  static const bool v = [] {
+    const char* e = getenv("SB200_ELECT_ISSUE");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
+  const bool elect = elect_issue_default() != ((p.debug & 32) != 0);  // debug bit 32 flips the default
   const bool has_lora = p.flags & SB200_EPI_LORA;
   p.b_rows = p.bn / ctas;
   p.l_rows = has_lora ? p.lora_rt / ctas : 0;
@@ -550,14 +582,19 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
   p.stages = stages;
   const int smem = kBarRegion + 1024 + stages * p.stage_bytes + kEpiBytes;
   if (!ctx->gemm_attr_set) {
-    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     ctx->gemm_attr_set = true;
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   if (ctas == 1) {
     const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-    gemm_kernel<1><<<grid, kGemmThreads, smem, stream>>>(p);
+    if (elect)
+      gemm_kernel<1, true><<<grid, kGemmThreads, smem, stream>>>(p);
+    else
+      gemm_kernel<1, false><<<grid, kGemmThreads, smem, stream>>>(p);
   } else {
     const int units = ctx->num_sms / 2;
     const int grid = 2 * (total < units ? total : units);
@@ -574,7 +611,10 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    SB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<2>, p));
+    if (elect)
+      SB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<2, true>, p));
+    else
+      SB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<2, false>, p));
   }
   SB200_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -593,7 +633,7 @@ static int check_lora(const sb200_lora* l, int N) {
 // bn encodes an explicit choice when > 0: low 12 bits = tile width, bit 12 set = force the CTA-pair kernel,
 // bit 13 set = force the single-CTA kernel (used by the tests to cover both).
 static void decode_bn(int bn_arg, int* bn, int* force_ctas, int* debug = nullptr) {
-  if (debug) *debug = bn_arg > 0 ? (bn_arg >> 14) & 3 : 0;
+  if (debug) *debug = bn_arg > 0 ? (bn_arg >> 14) & 63 : 0;
   *force_ctas = (bn_arg > 0 && (bn_arg & 0x1000)) ? 2 : ((bn_arg > 0 && (bn_arg & 0x2000)) ? 1 : 0);
   *bn = bn_arg > 0 ? (bn_arg & 0xFFF) : 0;
 }

@@ -207,3 +207,30 @@ def test_fanout_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "ok" in o, o
+
+
+def test_launch_plan_dry_run_counts_and_flops():
+    """Dry-run the SDXL forward on the meta device with shape-recording stand-ins for the kernels: the launch plan
+    must contain every Linear/conv FLOP of SURVEY.md §8d (6.761 TFLOP per pass incl. attention) and the fusions
+    DESIGN.md claims (one GEMM per fused QKV, cross-attention K/V batched, LoRA folded: no extra launches)."""
+    import importlib
+    import subprocess
+    import sys as _sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tools');"
+        "import shape_trace as st;"
+        "tr = st.trace(2);"
+        "import collections;"
+        "k = collections.Counter(n for n, _, _ in tr);"
+        "fl = sum(f for _, _, f in tr);"
+        "print(len(tr), k['gemm_kernel'], k['attention_kernel'], k['layernorm_kernel'], fl)" % (ROOT, ROOT))
+    out = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    n, n_gemm, n_attn, n_ln, flops = out.stdout.strip().splitlines()[-1].split()
+    assert int(n_attn) == 140 and int(n_ln) == 210
+    # 743 Linear + 51 3x3/1x1 convs - fused QKV (2 x 70 saved) - batched cross K/V (140 -> 2) - small linears ...
+    assert int(n_gemm) == 493
+    assert int(n) == 1008
+    per_pass = float(flops) / 2
+    assert abs(per_pass - 6.761e12) / 6.761e12 < 0.01, per_pass

@@ -15,11 +15,11 @@ dev = torch.device("cuda:0")
 s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def t(M, N, K, bn, debug, iters=20):
+def t(M, N, K, bn, debug, iters=20, force=0x2000):
     x = torch.randn(M, K, device=dev).to(torch.bfloat16)
     w = torch.randn(N, K, device=dev).to(torch.bfloat16)
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    arg = bn | 0x2000 | (debug << 14)
+    arg = bn | force | (debug << 14)
     call = lambda: lib.sb200_gemm(h, s, x.data_ptr(), K, None, 0, K, w.data_ptr(), K, out.data_ptr(), N, M, N, K, 0,
                                   None, None, 1, None, 0, None, arg)
     for _ in range(3):
@@ -35,10 +35,14 @@ def t(M, N, K, bn, debug, iters=20):
     return us, 2.0 * M * N * K / us / 1e6
 
 
-for (M, N, K) in ((8192, 8192, 8192), (8192, 1280, 1280), (8192, 10240, 1280), (8192, 1280, 5120)):
-    for bn in (256, 128):
+mode = sys.argv[1] if len(sys.argv) > 1 else "single"
+FORCE = 0x1000 if mode == "pair" else 0x2000
+shapes = ((8192, 8192, 8192), (8192, 1280, 1280)) if mode == "pair" else (
+    (8192, 8192, 8192), (8192, 1280, 1280), (8192, 10240, 1280), (8192, 1280, 5120))
+for (M, N, K) in shapes:
+    for bn in ((64, 128, 160, 192, 256) if mode == "pair" else (256, 128)):
         row = []
-        for debug, name in ((0, "full"), (1, "noW"), (2, "noA"), (3, "none")):
-            us, tf = t(M, N, K, bn, debug)
+        for debug, name in ((0, "lane0-issue"), (32, "elect-issue"), (0, "lane0 again"), (32, "elect again")):
+            us, tf = t(M, N, K, bn, debug, force=FORCE)
             row.append(f"{name} {us:8.1f}us {tf:6.0f}TF")
         print(f"M{M} N{N} K{K} bn{bn}: " + " | ".join(row), flush=True)
