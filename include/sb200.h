@@ -92,13 +92,13 @@ int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx0, const vo
                   int stride, int flags, const void* bias, const void* rowbias, const void* resid,
                   int ldr, const sb200_lora* lora, int bn);
 
-/* softmax(Q K^T * scale) V per (batch, head); head dim 64 (SDXL). Q/K/V/O are token matrices with row
- * strides in elements; head h occupies columns [h*64, h*64+64). Replaces the attention processor called
- * by diffusers Attention (xformers / SDPA; train_lora_xl.py:79-80).
+/* softmax(Q K^T * scale) V per (batch, head); head_dim a multiple of 8 up to 192 (SDXL 64; SD1.x 40 / 80 / 160).
+ * Q/K/V/O are token matrices with row strides in elements; head h occupies columns [h*head_dim, (h+1)*head_dim).
+ * Replaces the attention processor called by diffusers Attention (xformers / SDPA; train_lora_xl.py:79-80).
  *   Q: [B*Sq, ldq]  K,V: [B*Skv, ldk/ldv]  O: [B*Sq, ldo] */
 int sb200_attention(void* handle, void* stream, const void* q, int ldq, const void* k, int ldk,
                     const void* v, int ldv, void* o, int ldo, int B, int heads, int Sq, int Skv,
-                    float scale);
+                    int head_dim, float scale);
 
 /* GroupNorm (+ optional SiLU) over an NHWC tensor that may be the channel concat of two sources.
  * Replaces torch GroupNorm + SiLU in ResnetBlock2D / Transformer2DModel / conv_norm_out.

@@ -1,14 +1,18 @@
-// Flash-attention forward for sm_100a, head dim 64:  O = softmax(Q K^T * scale) V  per (batch, head).
+// Flash-attention forward for sm_100a:  O = softmax(Q K^T * scale) V  per (batch, head), head dim d <= 192
+// (SDXL: 64; SD1.x: 40 / 80 / 160).  The head dim is padded to ND x 64 columns by TMA's out-of-bounds zero
+// fill: Q/K/V are addressed through 4-D descriptors (d, heads, tokens, batch), so a 64-wide box that sticks out
+// of a 40- or 80-wide head reads zeros, never the neighbouring head.
 //
-// One CTA per (128-query tile, head, batch); two CTAs are resident per SM (256 TMEM columns, ~81 KB smem
-// each) so one CTA's tensor-core work overlaps the other's softmax.
-//   warp 0      TMA producer: Q tile once, then K / V tiles (128 keys x 64) through 2-stage rings
-//   warp 1      MMA issuer  : S = Q K^T   (tcgen05.mma SS, 128x128x64, fp32 in TMEM columns [0,128))
-//                             O += P V    (tcgen05.mma TS: P read from TMEM, V MN-major from smem)
-//   warps 2..5  softmax     : one query row per thread. Two passes over S in TMEM (row max, then
-//                             exp2 + bf16 pack), P written back to TMEM columns [128,192) as the A
-//                             operand of the PV MMA; the O accumulator (columns [192,256)) stays in TMEM
-//                             and is rescaled lazily (only when the running max grows by > 2^8).
+// One CTA per (128-query tile, head, batch).  ND = 1: two CTAs resident per SM (256 TMEM columns, ~81 KB smem
+// each) so one CTA's tensor-core work overlaps the other's softmax; ND = 2, 3: one CTA per SM.
+//   warp 0      TMA producer: Q tile once, then K / V tiles (128 keys x ND x 64) through a ring of stages
+//   warp 1      MMA issuer  : S = Q K^T   (tcgen05.mma SS, 128x128x16 per k-step, fp32 in TMEM columns [0,128))
+//                             O += P V    (tcgen05.mma TS: P read from TMEM, V MN-major from smem, N = 64 per
+//                                          sub-tile of the head dim)
+//   warps 2..5  softmax     : one query row per thread. Two passes over S in TMEM (row max, then exp2 + bf16
+//                             pack), P written back to TMEM columns [128,192) as the A operand of the PV MMA; the
+//                             O accumulator (columns [192, 192 + 64 ND)) stays in TMEM and is rescaled lazily
+//                             (only when the running max grows by > 2^8).
 // Keys beyond Skv (cross-attention: 77) are masked to -inf; TMA zero-fills the out-of-range rows.
 //
 // Replaces the attention processor that diffusers' Attention calls (xformers memory_efficient_attention /
@@ -19,16 +23,23 @@
 namespace sb200 {
 
 constexpr int kAttnThreads = 192;
-constexpr int kAttnStages = 2;
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
-constexpr int kAttnSmem = kTileBytes * (1 + 2 * kAttnStages) + 1024 /*barriers*/ + 1024 /*align*/;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
+
+template <int ND>
+struct AttnCfg {
+  static constexpr int kStages = ND == 3 ? 1 : 2;
+  static constexpr int kSmem = kTileBytes * ND * (1 + 2 * kStages) + 1024 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kTmemCols = ND == 1 ? 256 : 512;
+  static constexpr int kMinBlocks = ND == 1 ? 2 : 1;
+};
 
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
   __nv_bfloat16* o;
   int ldo;
   int Sq, Skv;
+  int d;           // head dim (multiple of 8)
   int n_kv_tiles;
   float scale_log2;  // scale * log2(e)
 };
@@ -39,7 +50,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+template <int ND>
+__global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
+    attention_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int kStages = AttnCfg<ND>::kStages;
+  constexpr uint32_t kStageBytes = kTileBytes * ND;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -50,20 +65,19 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
 
   const uint32_t sQ = base;
-  const uint32_t sK = base + kTileBytes;
-  const uint32_t sV = sK + kAttnStages * kTileBytes;
-  const uint32_t bars = sV + kAttnStages * kTileBytes;
+  const uint32_t sK = base + kStageBytes;
+  const uint32_t sV = sK + kStages * kStageBytes;
+  const uint32_t bars = sV + kStages * kStageBytes;
   const uint32_t bar_q = bars;
-  const uint32_t bar_kfull = bars + 8;                       // kAttnStages
-  const uint32_t bar_kempty = bar_kfull + 8 * kAttnStages;   // kAttnStages
-  const uint32_t bar_vfull = bar_kempty + 8 * kAttnStages;
-  const uint32_t bar_vempty = bar_vfull + 8 * kAttnStages;
-  const uint32_t bar_sfull = bar_vempty + 8 * kAttnStages;
+  const uint32_t bar_kfull = bars + 8;                   // kStages
+  const uint32_t bar_kempty = bar_kfull + 8 * kStages;   // kStages
+  const uint32_t bar_vfull = bar_kempty + 8 * kStages;
+  const uint32_t bar_vempty = bar_vfull + 8 * kStages;
+  const uint32_t bar_sfull = bar_vempty + 8 * kStages;
   const uint32_t bar_sfree = bar_sfull + 8;
   const uint32_t bar_pfull = bar_sfree + 8;
   const uint32_t bar_pvdone = bar_pfull + 8;
-  volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem + (bars - base) + 512);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bars - base) + 512);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -72,7 +86,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar_q, 1);
-    for (int i = 0; i < kAttnStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(bar_kfull + 8 * i, 1);
       mbar_init(bar_kempty + 8 * i, 1);
       mbar_init(bar_vfull + 8 * i, 1);
@@ -85,7 +99,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 256);
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), AttnCfg<ND>::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -93,28 +107,34 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n = p.n_kv_tiles;
+  const int dsteps = (p.d + 15) >> 4;  // 16-wide k-steps of the QK^T contraction that hold data
 
   if (warp == 0) {
     // converged warp, one ELECTed lane issues (a `lane == 0` branch makes ptxas wrap every uniform-datapath
     // instruction in an ELECT / BRA.U.ANY retry loop)
     if (elect_one()) {
-      mbar_expect_tx(bar_q, kTileBytes);
-      tma_load_3d(sQ, &p.tmQ, bar_q, head * 64, qt * 128, b);
+      mbar_expect_tx(bar_q, kStageBytes);
+#pragma unroll
+      for (int i = 0; i < ND; ++i) tma_load_4d(sQ + i * kTileBytes, &p.tmQ, bar_q, i * 64, head, qt * 128, b);
     }
     __syncwarp();
     for (int j = 0; j < n; ++j) {
-      const int s = j % kAttnStages;
-      const uint32_t ph = (j / kAttnStages) & 1;
+      const int s = j % kStages;
+      const uint32_t ph = (j / kStages) & 1;
       mbar_wait(bar_kempty + 8 * s, ph ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(bar_kfull + 8 * s, kTileBytes);
-        tma_load_3d(sK + s * kTileBytes, &p.tmK, bar_kfull + 8 * s, head * 64, j * 128, b);
+        mbar_expect_tx(bar_kfull + 8 * s, kStageBytes);
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+          tma_load_4d(sK + s * kStageBytes + i * kTileBytes, &p.tmK, bar_kfull + 8 * s, i * 64, head, j * 128, b);
       }
       __syncwarp();
       mbar_wait(bar_vempty + 8 * s, ph ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(bar_vfull + 8 * s, kTileBytes);
-        tma_load_3d(sV + s * kTileBytes, &p.tmV, bar_vfull + 8 * s, head * 64, j * 128, b);
+        mbar_expect_tx(bar_vfull + 8 * s, kStageBytes);
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+          tma_load_4d(sV + s * kStageBytes + i * kTileBytes, &p.tmV, bar_vfull + 8 * s, i * 64, head, j * 128, b);
       }
       __syncwarp();
     }
@@ -123,17 +143,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);  // B (= V) is MN-major
     mbar_wait(bar_q, 0);
     for (int j = 0; j < n; ++j) {
-      const int s = j % kAttnStages;
-      const uint32_t ph = (j / kAttnStages) & 1;
+      const int s = j % kStages;
+      const uint32_t ph = (j / kStages) & 1;
       // ---- S_j = Q K_j^T
       mbar_wait(bar_kfull + 8 * s, ph);
       mbar_wait(bar_sfree, (j & 1) ^ 1u);  // softmax finished reading S_{j-1}
       tc_fence_after();
       if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_ss(tmem_base + kColS, umma_desc_sw128(sQ + k * 32),
-                  umma_desc_sw128(sK + s * kTileBytes + k * 32), idesc_qk, k != 0);
+        for (int k = 0; k < dsteps; ++k) {
+          const uint32_t off = static_cast<uint32_t>(k >> 2) * kTileBytes + static_cast<uint32_t>(k & 3) * 32;
+          umma_ss(tmem_base + kColS, umma_desc_sw128(sQ + off), umma_desc_sw128(sK + s * kStageBytes + off),
+                  idesc_qk, k != 0);
         }
         umma_commit(bar_kempty + 8 * s);
         umma_commit(bar_sfull);
@@ -147,8 +167,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         const int kv_left = p.Skv - j * 128;
         const int ksteps = kv_left >= 128 ? 8 : (kv_left + 15) >> 4;  // keys beyond Skv contribute nothing
         for (int k = 0; k < ksteps; ++k) {
-          umma_ts(tmem_base + kColO, tmem_base + kColP + k * 8,
-                  umma_desc_sw128(sV + s * kTileBytes + k * 2048), idesc_pv, (j | k) != 0);
+#pragma unroll
+          for (int i = 0; i < ND; ++i)
+            umma_ts(tmem_base + kColO + i * 64, tmem_base + kColP + k * 8,
+                    umma_desc_sw128(sV + s * kStageBytes + i * kTileBytes + k * 2048), idesc_pv, (j | k) != 0);
         }
         umma_commit(bar_vempty + 8 * s);
         umma_commit(bar_pvdone);
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         if (__any_sync(0xffffffffu, need)) {
           l_run *= alpha;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 2 * ND; ++c) {
             uint32_t o[32];
             tmem_ld_x32(tl + kColO + c * 32, o);
             tmem_ld_wait();
@@ -252,27 +274,30 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pfull);
     }
-    // ---- finalize: O / l -> bf16 -> global
+    // ---- finalize: O / l -> bf16 -> global (only the first d columns of the padded head)
     mbar_wait(bar_pvdone, (n - 1) & 1);
     tc_fence_after();
     const float inv = 1.f / l_run;
     const int srow = qt * 128 + row;
-    __nv_bfloat16* op =
-        p.o + (static_cast<size_t>(b) * p.Sq + srow) * p.ldo + head * 64;
+    __nv_bfloat16* op = p.o + (static_cast<size_t>(b) * p.Sq + srow) * p.ldo + head * p.d;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_x32(tl + kColO + c * 32, o);
-      tmem_ld_wait();
-      if (srow < p.Sq) {
+    for (int c = 0; c < 2 * ND; ++c) {
+      if (c * 32 < p.d) {  // warp-uniform
+        uint32_t o[32];
+        tmem_ld_x32(tl + kColO + c * 32, o);
+        tmem_ld_wait();
+        if (srow < p.Sq) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = w;
+          for (int i = 0; i < 4; ++i) {
+            if (c * 32 + i * 8 < p.d) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+              *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = w;
+            }
+          }
         }
       }
     }
@@ -282,8 +307,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, AttnCfg<ND>::kTmemCols);
   }
+}
+
+template <int ND>
+static int launch_attention(Ctx* ctx, cudaStream_t stream, const AttnParams& p, dim3 grid) {
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[ND]) {
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          AttnCfg<ND>::kSmem));
+    attr_set[ND] = true;
+  }
+  attention_kernel<ND><<<grid, kAttnThreads, AttnCfg<ND>::kSmem, stream>>>(p);
+  SB200_CUDA_CHECK(cudaGetLastError());
+  (void)ctx;
+  return 0;
 }
 
 }  // namespace sb200
@@ -292,45 +331,46 @@ using namespace sb200;
 
 extern "C" int sb200_attention(void* handle, void* stream, const void* q, int ldq, const void* k, int ldk,
                                const void* v, int ldv, void* o, int ldo, int B, int heads, int Sq, int Skv,
-                               float scale) {
+                               int head_dim, float scale) {
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "attention: NULL handle");
   SB200_REQUIRE(B > 0 && heads > 0 && Sq > 0 && Skv > 0, "attention: bad dims");
+  SB200_REQUIRE(head_dim >= 8 && head_dim <= 192 && head_dim % 8 == 0,
+                "attention: head dim %d unsupported (multiple of 8, <= 192)", head_dim);
   SB200_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
                 "attention: leading dims must be multiples of 8");
-  SB200_REQUIRE(ldq >= heads * 64 && ldk >= heads * 64 && ldv >= heads * 64 && ldo >= heads * 64,
-                "attention: head dim is fixed at 64 (heads=%d needs >= %d columns)", heads, heads * 64);
+  SB200_REQUIRE(ldq >= heads * head_dim && ldk >= heads * head_dim && ldv >= heads * head_dim &&
+                    ldo >= heads * head_dim,
+                "attention: heads=%d x head_dim=%d exceeds a row", heads, head_dim);
   AttnParams p;
   memset(&p, 0, sizeof(p));
   int st;
-  const uint32_t box[3] = {64, 128, 1};
+  const uint32_t box[4] = {64, 1, 128, 1};
+  const uint64_t hs = static_cast<uint64_t>(head_dim) * 2;  // byte stride between heads
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(Sq),
-                              static_cast<uint64_t>(B)};
-    const uint64_t strides[2] = {static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(ldq) * 2 * Sq};
-    if ((st = make_tmap_bf16(ctx, &p.tmQ, q, 3, dims, strides, box))) return st;
+    const uint64_t dims[4] = {static_cast<uint64_t>(head_dim), static_cast<uint64_t>(heads),
+                              static_cast<uint64_t>(Sq), static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {hs, static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(ldq) * 2 * Sq};
+    if ((st = make_tmap_bf16(ctx, &p.tmQ, q, 4, dims, strides, box))) return st;
   }
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(Skv),
-                              static_cast<uint64_t>(B)};
-    const uint64_t sk[2] = {static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(ldk) * 2 * Skv};
-    const uint64_t sv[2] = {static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(ldv) * 2 * Skv};
-    if ((st = make_tmap_bf16(ctx, &p.tmK, k, 3, dims, sk, box))) return st;
-    if ((st = make_tmap_bf16(ctx, &p.tmV, v, 3, dims, sv, box))) return st;
+    const uint64_t dims[4] = {static_cast<uint64_t>(head_dim), static_cast<uint64_t>(heads),
+                              static_cast<uint64_t>(Skv), static_cast<uint64_t>(B)};
+    const uint64_t sk[3] = {hs, static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(ldk) * 2 * Skv};
+    const uint64_t sv[3] = {hs, static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(ldv) * 2 * Skv};
+    if ((st = make_tmap_bf16(ctx, &p.tmK, k, 4, dims, sk, box))) return st;
+    if ((st = make_tmap_bf16(ctx, &p.tmV, v, 4, dims, sv, box))) return st;
   }
   p.o = static_cast<__nv_bfloat16*>(o);
   p.ldo = ldo;
   p.Sq = Sq;
   p.Skv = Skv;
+  p.d = head_dim;
   p.n_kv_tiles = (Skv + 127) / 128;
   p.scale_log2 = scale * 1.4426950408889634f;
-  if (!ctx->attn_attr_set) {
-    SB200_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kAttnSmem));
-    ctx->attn_attr_set = true;
-  }
   dim3 grid((Sq + 127) / 128, heads, B);
-  attention_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
-  SB200_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (head_dim <= 64) return launch_attention<1>(ctx, s, p, grid);
+  if (head_dim <= 128) return launch_attention<2>(ctx, s, p, grid);
+  return launch_attention<3>(ctx, s, p, grid);
 }

@@ -128,13 +128,15 @@ def conv3x3(x0: torch.Tensor, w_packed: torch.Tensor, *, x1: Optional[torch.Tens
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, Sq: int, Skv: int,
-              scale: float) -> torch.Tensor:
-    """q/k/v: 2-D (possibly column-sliced) token matrices, head dim 64.  One `attention_kernel`."""
-    out = torch.empty((B * Sq, heads * 64), device=q.device, dtype=BF16)
+              scale: float, head_dim: int = 64) -> torch.Tensor:
+    """q/k/v: 2-D (possibly column-sliced) token matrices; head h = columns [h*head_dim, (h+1)*head_dim).
+    One `attention_kernel`."""
+    out = torch.empty((B * Sq, heads * head_dim), device=q.device, dtype=BF16)
     lib = _begin()
     _cabi.check(lib.sb200_attention(_ctx(q), _stream(), _p(q), q.stride(0), _p(k), k.stride(0), _p(v),
-                                    v.stride(0), _p(out), out.stride(0), B, heads, Sq, Skv, float(scale)))
-    _count("attention", 4.0 * B * heads * Sq * Skv * 64)
+                                    v.stride(0), _p(out), out.stride(0), B, heads, Sq, Skv, int(head_dim),
+                                    float(scale)))
+    _count("attention", 4.0 * B * heads * Sq * Skv * head_dim)
     return out
 
 

@@ -481,14 +481,11 @@ class UNet2DConditionModel(nn.Module):
     def _attn(self, attn: Attention, x_norm, resid, B, S, ctx=None, Sctx=0, kv_all=None):
         """x_norm: [B*S, C] normalised input; returns resid + to_out(attention)."""
         C_ = attn.to_q.weight.shape[0]
-        if attn.dim_head != 64:
-            raise NotImplementedError(f"attention head dim {attn.dim_head}: the flash kernel is built for 64 "
-                                      "(SDXL); SD1.x head dims 40/80/160 are a later row of SURVEY.md §8f")
         scale = attn.dim_head ** -0.5
         if ctx is None:
             leaves = [attn.to_q, attn.to_k, attn.to_v]
             qkv = ops.gemm(x_norm, self._fused_w(leaves), lora=self._lora(leaves))
-            o = ops.attention(qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:], B, attn.heads, S, S, scale)
+            o = ops.attention(qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:], B, attn.heads, S, S, scale, attn.dim_head)
         else:
             q = ops.gemm(x_norm, self._w(attn.to_q), lora=self._lora([attn.to_q]))
             if kv_all is not None:
@@ -499,7 +496,7 @@ class UNet2DConditionModel(nn.Module):
                 kvl = [attn.to_k, attn.to_v]
                 kv = ops.gemm(ctx, self._fused_w(kvl), lora=self._lora(kvl))
                 k, v = kv[:, :C_], kv[:, C_:]
-            o = ops.attention(q, k, v, B, attn.heads, S, Sctx, scale)
+            o = ops.attention(q, k, v, B, attn.heads, S, Sctx, scale, attn.dim_head)
         out = attn.to_out[0]
         return ops.gemm(o, self._w(out), bias=self._b(out), resid=resid, lora=self._lora([out]))
 

@@ -298,3 +298,31 @@ def test_bad_arguments_return_errors_not_crashes(dev):
         ops.conv3x3(torch.zeros(1, 96, 96, 64, device=dev, dtype=BF), torch.zeros(64, 3, 3, 64, device=dev, dtype=BF))
     with pytest.raises(_cabi.Sb200Error, match="CUDA tensors"):
         ops.layernorm(torch.zeros(4, 64, dtype=BF), torch.zeros(64, dtype=BF), torch.zeros(64, dtype=BF))
+
+
+@pytest.mark.parametrize("B,heads,Sq,Skv,d", [
+    (2, 8, 4096, 4096, 40),   # SD1.x 64x64 level
+    (2, 8, 1024, 77, 40),
+    (2, 8, 1024, 1024, 80),   # 32x32 level
+    (2, 8, 256, 256, 160),    # 16x16 level
+    (3, 8, 64, 64, 160),      # 8x8 level: fewer queries / keys than a tile
+    (2, 8, 256, 77, 160),
+    (1, 5, 320, 200, 24),     # any multiple of 8 works
+])
+def test_attention_sd1_head_dims(dev, B, heads, Sq, Skv, d):
+    """Head dims that are not 64: the kernel pads the head to 64 / 128 / 192 columns with TMA zero fill."""
+    from sliders_b200 import ops
+
+    g = torch.Generator().manual_seed(Sq + d)
+    Cc = heads * d
+    q = torch.randn(B * Sq, Cc, generator=g).to(dev, BF)
+    kv = torch.randn(B * Skv, 2 * Cc, generator=g).to(dev, BF)
+    k, v = kv[:, :Cc], kv[:, Cc:]
+    scale = d ** -0.5
+    out = ops.attention(q, k, v, B, heads, Sq, Skv, scale, head_dim=d)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, Sq, heads, d).transpose(1, 2)
+    kf = k.float().reshape(B, Skv, heads, d).transpose(1, 2)
+    vf = v.float().reshape(B, Skv, heads, d).transpose(1, 2)
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * scale, dim=-1) @ vf).transpose(1, 2).reshape(B * Sq, Cc)
+    assert rel_rms(out, ref) < 2e-2

@@ -281,3 +281,42 @@ def test_denoise_loop_with_slider_gating(dev):
                                   start_noise=start_noise)
     pm.use_cuda_graph = False
     assert torch.equal(got_g, got)
+
+
+def test_full_sd15_parity_vs_fp32_oracle(dev):
+    """BASELINE config 2: SD-1.x UNet (859.5 M parameters, head dims 40 / 80 / 160, 1x1-conv projections, 8x8
+    bottleneck), 64x64 latents (512 px), rank-4 LoRA on 150 leaves, CFG pair through `predict_noise`."""
+    from oracle import unet as ounet
+    from sliders_b200 import lora as plora, synthetic, train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    with torch.device(dev):
+        pm = UNet2DConditionModel(UNetConfig.sd15()).to(BF)
+        om = ounet.UNet2DConditionModel(ounet.UNetConfig.sd15())
+    synthetic.init_synthetic_(pm, seed=5)
+    om.load_state_dict({k: v.float() for k, v in pm.state_dict().items()})
+    om.eval()
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+    assert len(net.unet_loras) == 150
+    synthetic.init_lora_nonzero_(net, seed=6, up_std=0.05)
+    mods = {("lora_unet_" + n.replace(".", "_")): m for n, m in om.named_modules()}
+    sd = net.state_dict()
+    with torch.no_grad():
+        for l in net.unet_loras:
+            up, down = sd[l.lora_name + ".lora_up.weight"].float(), sd[l.lora_name + ".lora_down.weight"].float()
+            delta = torch.einsum("or,rikl->oikl", up[:, :, 0, 0], down) if down.dim() == 4 else up @ down
+            mods[l.lora_name].weight.add_(delta * l.scale)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(2, 4, 64, 64, generator=g).to(dev, BF)
+    ehs = torch.randn(4, 77, 768, generator=g).to(dev, BF)  # [u, u, c, c]
+    sched = create_noise_scheduler("ddim")
+    sched.set_timesteps(1000)
+    with torch.no_grad():
+        out = om(torch.cat([lat.float()] * 2), 321, ehs.float()).sample
+        u, c = out.chunk(2)
+        ref = u + 1.0 * (c - u)
+        with net:
+            got = train_util.predict_noise(pm, sched, 321, lat, ehs, guidance_scale=1.0)
+    assert rel_rms(got, ref) < 2.5e-2

@@ -24,5 +24,5 @@ else:
     q, k, v, ld, ldk = qkv, kv, kv[:, Cc:], 3 * Cc, 2 * Cc
 for _ in range(3):
     _cabi.check(lib.sb200_attention(h, s, q.data_ptr(), ld, k.data_ptr(), ldk, v.data_ptr(), ldk, o.data_ptr(), Cc, B,
-                                    heads, Sq, Skv, 0.125))
+                                    heads, Sq, Skv, 64, 0.125))
 torch.cuda.synchronize()

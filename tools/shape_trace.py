@@ -42,7 +42,7 @@ def conv3x3(x0, w, *, x1=None, stride=1, bias=None, rowbias=None, resid=None, lo
     return _meta(B, H // stride, W // stride, Cout)
 
 
-def attention(q, k, v, B, heads, Sq, Skv, scale):
+def attention(q, k, v, B, heads, Sq, Skv, scale, head_dim=64):
     calls.append(("attention_kernel", f"attn B{B} h{heads} Sq{Sq} Skv{Skv}", 4.0 * B * heads * Sq * Skv * 64))
     return _meta(B * Sq, heads * 64)
 
