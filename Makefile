@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall \
              --expt-relaxed-constexpr -Xptxas -v
 CSRC      := sliders_b200/csrc
-SRCS      := $(CSRC)/api.cu $(CSRC)/gemm.cu $(CSRC)/attention.cu $(CSRC)/norm.cu $(CSRC)/elementwise.cu
+SRCS      := $(CSRC)/api.cu $(CSRC)/gemm.cu $(CSRC)/attention.cu $(CSRC)/norm.cu $(CSRC)/elementwise.cu $(CSRC)/attention_bwd.cu $(CSRC)/backward.cu
 OBJS      := $(SRCS:.cu=.o)
 LIB       := sliders_b200/libsb200.so
 

@@ -98,7 +98,83 @@ int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx0, const vo
  *   Q: [B*Sq, ldq]  K,V: [B*Skv, ldk/ldv]  O: [B*Sq, ldo] */
 int sb200_attention(void* handle, void* stream, const void* q, int ldq, const void* k, int ldk,
                     const void* v, int ldv, void* o, int ldo, int B, int heads, int Sq, int Skv,
-                    int head_dim, float scale);
+                    int head_dim, float scale, float* lse /* optional [B, heads, Sq] fp32, for sb200_attention_bwd */);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backward-to-LoRA pass: `loss.backward()` at trainscripts/textsliders/train_lora_xl.py:345 (train_lora.py:298,
+ * imagesliders/train_lora-scale-xl.py:340,372) through the frozen UNet to the lora_down / lora_up weights
+ * (lora.py:108-112), and `optimizer.step()` (:346; AdamW built at train_util.py:362-363).
+ * Dense input gradients reuse sb200_gemm / sb200_conv3x3 with transposed weights (dX = dY W; for a 3x3 conv the
+ * flipped-tap, channel-transposed weight; for stride 2 on the sb200_zero_stuff'ed gradient).
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* Flash-attention backward.  q/k/v/o/dout and lse as in sb200_attention; dsum: caller scratch [B*heads*Sq] fp32.
+ * dq always; dk and dv both or neither (NULL for cross-attention whose K/V need no gradient). */
+int sb200_attention_bwd(void* handle, void* stream, const void* q, int ldq, const void* k, int ldk, const void* v,
+                        int ldv, const void* o, int ldo, const void* dout, int lddo, const float* lse, float* dsum,
+                        void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B, int heads, int Sq,
+                        int Skv, int head_dim, float scale);
+
+/* GroupNorm(+SiLU) backward w.r.t. the input (gamma / beta are frozen).  fwd_stats: the [B][groups][2] (mean, rstd)
+ * block the forward left at stats_ws + SB200_GN_STATS_OFFSET(B, groups); ws: SB200_GN_WS_FLOATS scratch.
+ * dx = dGN(dy) (+ add), written as the channel concat [B, HW, C0 + C1] with row stride lddx. */
+#define SB200_GN_STATS_OFFSET(B, groups) ((size_t)(B) * (groups) * 2 * 128)
+int sb200_groupnorm_bwd(void* handle, void* stream, const void* x0, int ldx0, int C0, const void* x1, int ldx1,
+                        int C1, const void* gamma, const void* beta, const void* dy, int lddy, const void* add,
+                        int ldadd, void* dx, int lddx, int B, int HW, int groups, int silu, const float* fwd_stats,
+                        float* ws);
+
+/* LayerNorm backward w.r.t. the input: dx = dLN(dy) (+ add). */
+int sb200_layernorm_bwd(void* handle, void* stream, const void* x, int ldx, const void* gamma, const void* dy,
+                        int lddy, const void* add, int ldadd, void* dx, int lddx, int M, int C, float eps);
+
+/* Unfused GEGLU for the training forward (pre = [a | g], out = a * gelu(g)) and its backward. */
+int sb200_geglu(void* handle, void* stream, const void* pre, int ldp, void* out, int ldo, int M, int F);
+int sb200_geglu_bwd(void* handle, void* stream, const void* pre, int ldp, const void* dout, int lddo, void* dpre,
+                    int lddp, int M, int F);
+
+/* out = a + b (+ c): gradient joins at residual / skip connections (2-D bf16, row strides in elements). */
+int sb200_add(void* handle, void* stream, const void* a, int lda, const void* b, int ldb, const void* c, int ldc,
+              void* out, int ldo, int M, int C);
+
+/* Upsample2D (nearest x2) backward: dy [B,2H,2W,C] -> dx [B,H,W,C]. */
+int sb200_upsample2x_bwd(void* handle, void* stream, const void* dy, void* dx, int B, int H, int W, int C);
+/* z[b,2i,2j,:] = dy[b,i,j,:], zeros elsewhere ([B,2Ho,2Wo,C]): input of the stride-1 conv that yields the input
+ * gradient of a stride-2 conv (Downsample2D). */
+int sb200_zero_stuff(void* handle, void* stream, const void* dy, void* z, int B, int Ho, int Wo, int C);
+/* conv_out (C -> 4, 3x3) backward: d_eps NCHW [B,4,H,W] (fp32 or bf16) -> dx NHWC [B,H,W,C]. w: [4,3,3,C]. */
+int sb200_conv_out_bwd(void* handle, void* stream, const void* deps, int deps_f32, const void* w, void* dx, int B,
+                       int H, int W, int C);
+/* out[b, c] = sum_hw dy[b, hw, c] (fp32): gradient reaching time_emb_proj's output. */
+int sb200_colsum(void* handle, void* stream, const void* dy, int ld, float* out, int B, int HW, int C);
+
+/* Rank-r (r = 4 or 8) LoRA gradient pieces for y = W x + s * up (down x), lora.py:108-112:
+ *   t = x down^T, u = dY up        : sb200_lora_proj   (T[M,r] (+)= A[M,C] Bt[r,C]^T, fp32 out)
+ *   d_up = s dY^T t, d_down = s u^T x : sb200_lora_wgrad  (G[c*gs_c + j*gs_r] (+)= scale * sum_m A[m,c] T[m,j])
+ *   dX += s u down                 : sb200_lora_rank_update
+ * and the 3x3-conv forms (down is a 3x3 conv with the leaf's stride, D = lora_down packed [r,3,3,C]).
+ * ws: SB200_WGRAD_WS_FLOATS(C, r) floats (C = 9 * channels for the conv form). */
+#define SB200_WGRAD_CBLOCKS(C) (((C) / 8 + 31) / 32)
+#define SB200_WGRAD_CHUNKS(cblocks) ((296 + (cblocks) - 1) / (cblocks) > 256 ? 256 : (296 + (cblocks) - 1) / (cblocks))
+#define SB200_WGRAD_WS_FLOATS(C, r) ((size_t)SB200_WGRAD_CHUNKS(SB200_WGRAD_CBLOCKS(C)) * (C) * (r))
+int sb200_lora_proj(void* handle, void* stream, const void* A, int lda, const void* Bt, int ldb, float* T, int M,
+                    int C, int r, int accumulate);
+int sb200_lora_wgrad(void* handle, void* stream, const void* A, int lda, const float* T, float* G, int gs_c,
+                     int gs_r, float scale, int accumulate, int M, int C, int r, float* ws);
+int sb200_lora_rank_update(void* handle, void* stream, void* dX, int ldx, const float* U, const void* D, int ldd,
+                           float scale, int M, int C, int r);
+int sb200_lora_conv_proj(void* handle, void* stream, const void* x0, int ldx0, int C0, const void* x1, int ldx1,
+                         int C1, const void* D, float* T, int B, int H, int W, int stride, int r);
+int sb200_lora_conv_wgrad(void* handle, void* stream, const void* x0, int ldx0, int C0, const void* x1, int ldx1,
+                          int C1, const float* U, float* G, float scale, int accumulate, int B, int H, int W,
+                          int stride, int r, float* ws);
+int sb200_lora_conv_rank_update(void* handle, void* stream, void* dX, const float* U, const void* D, float scale,
+                                int B, int H, int W, int C, int stride, int r);
+
+/* torch.optim.AdamW step on bf16 parameters with bf16 moments (every intermediate torch materialises as a bf16
+ * tensor is rounded to bf16).  table: device array of n_tensors records {p, g, m, v: device pointers; n: int64}. */
+int sb200_adamw(void* handle, void* stream, const void* table, int n_tensors, long long max_numel, double lr,
+                double beta1, double beta2, double eps, double weight_decay, int step);
 
 /* GroupNorm (+ optional SiLU) over an NHWC tensor that may be the channel concat of two sources.
  * Replaces torch GroupNorm + SiLU in ResnetBlock2D / Transformer2DModel / conv_norm_out.

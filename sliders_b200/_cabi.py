@@ -32,7 +32,7 @@ class LoraArgs(C.Structure):
     ]
 
 
-_p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+_p, _i, _f, _i64, _d = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_double
 _LP = C.POINTER(LoraArgs)
 
 # name -> argtypes (restype is int unless listed in _RESTYPE)
@@ -44,7 +44,25 @@ SIGNATURES = {
     "sb200_gemm": [_p, _p, _p, _i, _p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _LP, _i],
     "sb200_conv3x3": [_p, _p, _p, _i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i,
                       _LP, _i],
-    "sb200_attention": [_p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _f],
+    "sb200_attention": [_p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _f, _p],
+    "sb200_attention_bwd": [_p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _p, _i, _p, _i, _p, _i,
+                            _i, _i, _i, _i, _i, _f],
+    "sb200_groupnorm_bwd": [_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p],
+    "sb200_layernorm_bwd": [_p, _p, _p, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _f],
+    "sb200_geglu": [_p, _p, _p, _i, _p, _i, _i, _i],
+    "sb200_geglu_bwd": [_p, _p, _p, _i, _p, _i, _p, _i, _i, _i],
+    "sb200_add": [_p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _i, _i],
+    "sb200_upsample2x_bwd": [_p, _p, _p, _p, _i, _i, _i, _i],
+    "sb200_zero_stuff": [_p, _p, _p, _p, _i, _i, _i, _i],
+    "sb200_conv_out_bwd": [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i],
+    "sb200_colsum": [_p, _p, _p, _i, _p, _i, _i, _i],
+    "sb200_lora_proj": [_p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i],
+    "sb200_lora_wgrad": [_p, _p, _p, _i, _p, _p, _i, _i, _f, _i, _i, _i, _i, _p],
+    "sb200_lora_rank_update": [_p, _p, _p, _i, _p, _p, _i, _f, _i, _i, _i],
+    "sb200_lora_conv_proj": [_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i],
+    "sb200_lora_conv_wgrad": [_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _f, _i, _i, _i, _i, _i, _i, _p],
+    "sb200_lora_conv_rank_update": [_p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i],
+    "sb200_adamw": [_p, _p, _p, _i, C.c_longlong, _d, _d, _d, _d, _d, _i],
     "sb200_groupnorm": [_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p],
     "sb200_layernorm": [_p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _f],
     "sb200_small_linear": [_p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _LP, _p],

@@ -37,6 +37,7 @@ struct AttnCfg {
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
   __nv_bfloat16* o;
+  float* lse;      // optional [B, heads, Sq]: log2-domain log-sum-exp of scale*log2(e)*S (for attention_bwd.cu)
   int ldo;
   int Sq, Skv;
   int d;           // head dim (multiple of 8)
@@ -279,6 +280,8 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
     tc_fence_after();
     const float inv = 1.f / l_run;
     const int srow = qt * 128 + row;
+    if (p.lse != nullptr && srow < p.Sq)
+      p.lse[(static_cast<size_t>(b) * gridDim.y + head) * p.Sq + srow] = m_run + log2f(l_run);
     __nv_bfloat16* op = p.o + (static_cast<size_t>(b) * p.Sq + srow) * p.ldo + head * p.d;
 #pragma unroll
     for (int c = 0; c < 2 * ND; ++c) {
@@ -331,7 +334,7 @@ using namespace sb200;
 
 extern "C" int sb200_attention(void* handle, void* stream, const void* q, int ldq, const void* k, int ldk,
                                const void* v, int ldv, void* o, int ldo, int B, int heads, int Sq, int Skv,
-                               int head_dim, float scale) {
+                               int head_dim, float scale, float* lse) {
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "attention: NULL handle");
   SB200_REQUIRE(B > 0 && heads > 0 && Sq > 0 && Skv > 0, "attention: bad dims");
@@ -362,6 +365,7 @@ extern "C" int sb200_attention(void* handle, void* stream, const void* q, int ld
     if ((st = make_tmap_bf16(ctx, &p.tmV, v, 4, dims, sv, box))) return st;
   }
   p.o = static_cast<__nv_bfloat16*>(o);
+  p.lse = lse;
   p.ldo = ldo;
   p.Sq = Sq;
   p.Skv = Skv;

@@ -16,7 +16,7 @@ BF16 = torch.bfloat16
 
 # launches issued through this module since import (bench.py reports it as gpu_launches)
 launch_count = 0
-_KERNELS_PER_CALL = {"groupnorm": 3}  # stats + finalize + apply
+_KERNELS_PER_CALL = {"groupnorm": 3, "groupnorm_bwd": 3, "lora_wgrad": 2}  # stats + finalize + apply; partial + reduce
 
 
 def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -128,14 +128,14 @@ def conv3x3(x0: torch.Tensor, w_packed: torch.Tensor, *, x1: Optional[torch.Tens
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, Sq: int, Skv: int,
-              scale: float, head_dim: int = 64) -> torch.Tensor:
+              scale: float, head_dim: int = 64, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q/k/v: 2-D (possibly column-sliced) token matrices; head h = columns [h*head_dim, (h+1)*head_dim).
-    One `attention_kernel`."""
+    One `attention_kernel`.  lse: optional fp32 [B, heads, Sq] output kept for `attention_bwd`."""
     out = torch.empty((B * Sq, heads * head_dim), device=q.device, dtype=BF16)
     lib = _begin()
     _cabi.check(lib.sb200_attention(_ctx(q), _stream(), _p(q), q.stride(0), _p(k), k.stride(0), _p(v),
                                     v.stride(0), _p(out), out.stride(0), B, heads, Sq, Skv, int(head_dim),
-                                    float(scale)))
+                                    float(scale), _p(lse)))
     _count("attention", 4.0 * B * heads * Sq * Skv * head_dim)
     return out
 
@@ -248,3 +248,220 @@ def cfg_ddim(eps2: torch.Tensor, guidance: float, x: Optional[torch.Tensor] = No
                                    int(out_dtype == torch.float32), n))
     _count()
     return eps_out, x_prev
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# backward-to-LoRA pass (csrc/backward.cu, csrc/attention_bwd.cu)
+# ----------------------------------------------------------------------------------------------------------------
+GN_STATS_OFFSET = 128  # final (mean, rstd) block sits at stats_ws[B * groups * 2 * 128:]  (SB200_GN_STATS_OFFSET)
+
+
+def gn_ws(B: int, groups: int, device) -> torch.Tensor:
+    return torch.empty(B * groups * 2 * 129, device=device, dtype=torch.float32)
+
+
+def attention_bwd(q, k, v, o, dout, lse, B: int, heads: int, Sq: int, Skv: int, scale: float, head_dim: int,
+                  dq: torch.Tensor, dk: Optional[torch.Tensor] = None, dv: Optional[torch.Tensor] = None) -> None:
+    """dq (and dk, dv) are 2-D (possibly column-sliced) outputs.  `attn_bwd_prep_kernel` + `attention_bwd_kernel`
+    (x2 when dk/dv are requested)."""
+    dsum = torch.empty(B * heads * Sq, device=q.device, dtype=torch.float32)
+    lib = _begin()
+    _cabi.check(lib.sb200_attention_bwd(
+        _ctx(q), _stream(), _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+        _p(dout), dout.stride(0), _p(lse), _p(dsum), _p(dq), dq.stride(0), _p(dk),
+        dk.stride(0) if dk is not None else 0, _p(dv), dv.stride(0) if dv is not None else 0, B, heads, Sq, Skv,
+        int(head_dim), float(scale)))
+    global launch_count
+    launch_count += 1 if dk is None else 2
+    _count("attention_bwd", (6.0 if dk is None else 14.0) * B * heads * Sq * Skv * head_dim)
+
+
+def groupnorm_bwd(x0, gamma, beta, groups: int, silu: bool, dy, stats_ws, *, x1=None, add=None) -> torch.Tensor:
+    """Input gradient of `groupnorm` (concat layout [.., C0 + C1]); stats_ws is the forward's workspace."""
+    shp = x0.shape
+    B, C0 = shp[0], shp[-1]
+    HW = x0.numel() // (B * C0)
+    C1 = x1.shape[-1] if x1 is not None else 0
+    Cc = C0 + C1
+    dx = torch.empty(shp[:-1] + (Cc,), device=x0.device, dtype=BF16)
+    ws = gn_ws(B, groups, x0.device)
+    fwd = stats_ws[B * groups * 2 * GN_STATS_OFFSET:]
+    lib = _begin()
+    _cabi.check(lib.sb200_groupnorm_bwd(
+        _ctx(x0), _stream(), _p(x0), x0.stride(-2), C0, _p(x1), x1.stride(-2) if x1 is not None else 0, C1,
+        _p(gamma), _p(beta), _p(dy), dy.stride(-2), _p(add), add.stride(-2) if add is not None else 0, _p(dx), Cc,
+        B, HW, groups, int(silu), _p(fwd), _p(ws)))
+    _count("groupnorm_bwd")
+    return dx
+
+
+def layernorm_bwd(x, gamma, dy, eps: float = 1e-5, add=None) -> torch.Tensor:
+    M, Cc = x.shape
+    dx = torch.empty((M, Cc), device=x.device, dtype=BF16)
+    lib = _begin()
+    _cabi.check(lib.sb200_layernorm_bwd(_ctx(x), _stream(), _p(x), x.stride(0), _p(gamma), _p(dy), dy.stride(0),
+                                        _p(add), add.stride(0) if add is not None else 0, _p(dx), Cc, M, Cc,
+                                        float(eps)))
+    _count()
+    return dx
+
+
+def geglu(pre: torch.Tensor) -> torch.Tensor:
+    M, F2 = pre.shape
+    out = torch.empty((M, F2 // 2), device=pre.device, dtype=BF16)
+    lib = _begin()
+    _cabi.check(lib.sb200_geglu(_ctx(pre), _stream(), _p(pre), pre.stride(0), _p(out), F2 // 2, M, F2 // 2))
+    _count()
+    return out
+
+
+def geglu_bwd(pre: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
+    M, F2 = pre.shape
+    dpre = torch.empty((M, F2), device=pre.device, dtype=BF16)
+    lib = _begin()
+    _cabi.check(lib.sb200_geglu_bwd(_ctx(pre), _stream(), _p(pre), pre.stride(0), _p(dout), dout.stride(0),
+                                    _p(dpre), F2, M, F2 // 2))
+    _count()
+    return dpre
+
+
+def add(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """a + b (+ c) on 2-D (row-strided) bf16 matrices."""
+    M, Cc = a.shape
+    if out is None:
+        out = torch.empty((M, Cc), device=a.device, dtype=BF16)
+    lib = _begin()
+    _cabi.check(lib.sb200_add(_ctx(a), _stream(), _p(a), a.stride(0), _p(b), b.stride(0), _p(c),
+                              c.stride(0) if c is not None else 0, _p(out), out.stride(0), M, Cc))
+    _count()
+    return out
+
+
+def upsample2x_bwd(dy: torch.Tensor) -> torch.Tensor:
+    B, H2, W2, Cc = dy.shape
+    dx = torch.empty((B, H2 // 2, W2 // 2, Cc), device=dy.device, dtype=BF16)
+    lib = _begin()
+    _cabi.check(lib.sb200_upsample2x_bwd(_ctx(dy), _stream(), _p(dy), _p(dx), B, H2 // 2, W2 // 2, Cc))
+    _count()
+    return dx
+
+
+def zero_stuff(dy: torch.Tensor) -> torch.Tensor:
+    B, Ho, Wo, Cc = dy.shape
+    z = torch.empty((B, 2 * Ho, 2 * Wo, Cc), device=dy.device, dtype=BF16)
+    lib = _begin()
+    _cabi.check(lib.sb200_zero_stuff(_ctx(dy), _stream(), _p(dy), _p(z), B, Ho, Wo, Cc))
+    _count()
+    return z
+
+
+def conv_out_bwd(deps: torch.Tensor, w_packed: torch.Tensor) -> torch.Tensor:
+    """deps: NCHW [B,4,H,W] fp32 / bf16 -> NHWC bf16 [B,H,W,C]."""
+    B, _, H, W = deps.shape
+    Cc = w_packed.shape[-1]
+    deps = deps.contiguous()
+    dx = torch.empty((B, H, W, Cc), device=deps.device, dtype=BF16)
+    lib = _begin()
+    _cabi.check(lib.sb200_conv_out_bwd(_ctx(deps), _stream(), _p(deps), int(deps.dtype == torch.float32),
+                                       _p(w_packed), _p(dx), B, H, W, Cc))
+    _count()
+    return dx
+
+
+def colsum(dy: torch.Tensor) -> torch.Tensor:
+    """dy [B, H, W, C] (or [B, HW, C]) -> fp32 [B, C]."""
+    B, Cc = dy.shape[0], dy.shape[-1]
+    HW = dy.numel() // (B * Cc)
+    out = torch.empty((B, Cc), device=dy.device, dtype=torch.float32)
+    lib = _begin()
+    _cabi.check(lib.sb200_colsum(_ctx(dy), _stream(), _p(dy), dy.stride(-2), _p(out), B, HW, Cc))
+    _count()
+    return out
+
+
+def _wgrad_ws(Cc: int, r: int, device) -> torch.Tensor:
+    cblocks = (Cc // 8 + 31) // 32
+    chunks = min(256, (296 + cblocks - 1) // cblocks)
+    return torch.empty(chunks * Cc * r, device=device, dtype=torch.float32)
+
+
+def lora_proj(A: torch.Tensor, Bt: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A [M, C] bf16 (row-strided), Bt [r, C] bf16 (row-strided) -> fp32 [M, r] = A @ Bt.T; with `out` given the
+    product is accumulated into it (two-source inputs: x = [x0 | x1])."""
+    M, Cc = A.shape
+    r = Bt.shape[0]
+    T = out if out is not None else torch.empty((M, r), device=A.device, dtype=torch.float32)
+    lib = _begin()
+    _cabi.check(lib.sb200_lora_proj(_ctx(A), _stream(), _p(A), A.stride(0), _p(Bt), Bt.stride(0), _p(T), M, Cc, r,
+                                    int(out is not None)))
+    _count()
+    return T
+
+
+def lora_wgrad(A: torch.Tensor, T: torch.Tensor, G: torch.Tensor, transposed: bool, scale: float,
+               accumulate: bool = False) -> None:
+    """G (+)= scale * A.T @ T.  A [M, C] bf16, T [M, r] fp32; G fp32 (any strides, e.g. a column slice):
+    [C, r] (transposed=False) or [r, C] (transposed=True)."""
+    M, Cc = A.shape
+    r = T.shape[1]
+    gs_c, gs_r = (G.stride(1), G.stride(0)) if transposed else (G.stride(0), G.stride(1))
+    ws = _wgrad_ws(Cc, r, A.device)
+    lib = _begin()
+    _cabi.check(lib.sb200_lora_wgrad(_ctx(A), _stream(), _p(A), A.stride(0), _p(T), _p(G), gs_c, gs_r, float(scale),
+                                     int(accumulate), M, Cc, r, _p(ws)))
+    _count("lora_wgrad")
+
+
+def lora_rank_update(dX: torch.Tensor, U: torch.Tensor, D: torch.Tensor, scale: float) -> None:
+    """dX += scale * U @ D   (dX [M, C] bf16 in place, U [M, r] fp32, D [r, C] bf16)."""
+    M, Cc = dX.shape
+    lib = _begin()
+    _cabi.check(lib.sb200_lora_rank_update(_ctx(dX), _stream(), _p(dX), dX.stride(0), _p(U), _p(D), D.stride(0),
+                                           float(scale), M, Cc, U.shape[1]))
+    _count()
+
+
+def lora_conv_proj(x0: torch.Tensor, D: torch.Tensor, stride: int = 1, x1: Optional[torch.Tensor] = None):
+    """3x3 / pad 1 conv of NHWC x (= [x0 | x1]) with D [r, 3, 3, C] -> fp32 [B*Ho*Wo, r]."""
+    B, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    r = D.shape[0]
+    T = torch.empty((B * (H // stride) * (W // stride), r), device=x0.device, dtype=torch.float32)
+    lib = _begin()
+    _cabi.check(lib.sb200_lora_conv_proj(_ctx(x0), _stream(), _p(x0), x0.stride(2), C0, _p(x1),
+                                         x1.stride(2) if x1 is not None else 0, C1, _p(D), _p(T), B, H, W, stride, r))
+    _count()
+    return T
+
+
+def lora_conv_wgrad(x0: torch.Tensor, U: torch.Tensor, G: torch.Tensor, scale: float, stride: int = 1,
+                    x1: Optional[torch.Tensor] = None, accumulate: bool = False) -> None:
+    """G [r, 3, 3, C] fp32 (+)= scale * sum_p U[p, :] (x) patch(x, p)."""
+    B, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    r = U.shape[1]
+    ws = _wgrad_ws(9 * (C0 + C1), r, x0.device)
+    lib = _begin()
+    _cabi.check(lib.sb200_lora_conv_wgrad(_ctx(x0), _stream(), _p(x0), x0.stride(2), C0, _p(x1),
+                                          x1.stride(2) if x1 is not None else 0, C1, _p(U), _p(G), float(scale),
+                                          int(accumulate), B, H, W, stride, r, _p(ws)))
+    _count("lora_wgrad")
+
+
+def lora_conv_rank_update(dX: torch.Tensor, U: torch.Tensor, D: torch.Tensor, scale: float, stride: int = 1) -> None:
+    """dX [B,H,W,C] (contiguous, in place) += scale * conv_transpose(U [B,Ho,Wo,r], D [r,3,3,C])."""
+    B, H, W, Cc = dX.shape
+    assert dX.is_contiguous()
+    lib = _begin()
+    _cabi.check(lib.sb200_lora_conv_rank_update(_ctx(dX), _stream(), _p(dX), _p(U), _p(D), float(scale), B, H, W, Cc,
+                                                stride, U.shape[1]))
+    _count()
+
+
+def adamw(table: torch.Tensor, n_tensors: int, max_numel: int, lr: float, beta1: float, beta2: float, eps: float,
+          weight_decay: float, step: int) -> None:
+    """One fused `adamw_kernel` launch over a device table of (p, g, m, v, n) records (int64 [n_tensors, 5])."""
+    lib = _begin()
+    _cabi.check(lib.sb200_adamw(_ctx(table), _stream(), _p(table), n_tensors, int(max_numel), float(lr), float(beta1),
+                                float(beta2), float(eps), float(weight_decay), int(step)))
+    _count()

@@ -46,11 +46,20 @@ def _unet_pair(unet, latents, timestep, text_embeddings, added_cond_kwargs=None)
     return unet(latent_model_input, timestep, encoder_hidden_states=text_embeddings, **kwargs).sample
 
 
+def _cfg(noise_pred: torch.Tensor, guidance_scale: float) -> torch.Tensor:
+    if noise_pred.requires_grad:
+        # grad-carrying prediction (train_lora_xl.py:299-322): the combine stays a torch op so autograd links the
+        # loss to the UNet node, whose backward is the sb200 backward pass (sliders_b200/autograd.py)
+        uncond, text = noise_pred.chunk(2)
+        return uncond + guidance_scale * (text - uncond)
+    guided, _ = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, out_dtype=noise_pred.dtype)
+    return guided
+
+
 def predict_noise(unet, scheduler, timestep, latents, text_embeddings, guidance_scale=7.5) -> torch.Tensor:
     latents = scheduler.scale_model_input(latents, timestep)
     noise_pred = _unet_pair(unet, latents, timestep, text_embeddings)
-    guided, _ = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, out_dtype=noise_pred.dtype)
-    return guided
+    return _cfg(noise_pred, guidance_scale)
 
 
 def predict_noise_xl(unet, scheduler, timestep, latents, text_embeddings, add_text_embeddings, add_time_ids,
@@ -58,8 +67,7 @@ def predict_noise_xl(unet, scheduler, timestep, latents, text_embeddings, add_te
     latents = scheduler.scale_model_input(latents, timestep)
     added = {"text_embeds": add_text_embeddings, "time_ids": add_time_ids}
     noise_pred = _unet_pair(unet, latents, timestep, text_embeddings, added)
-    guided, _ = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, out_dtype=noise_pred.dtype)
-    return guided
+    return _cfg(noise_pred, guidance_scale)
 
 
 def _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_scale, total_timesteps, start_timesteps):
@@ -103,3 +111,46 @@ def get_add_time_ids(height: int, width: int, dynamic_crops: bool = False, dtype
         raise ValueError(f"Model expects an added time embedding vector of length "
                          f"{UNET_PROJECTION_CLASS_EMBEDDING_INPUT_DIM}, but a vector of {passed} was created.")
     return torch.tensor([add_time_ids], dtype=dtype)
+
+
+def get_random_resolution_in_bucket(bucket_resolution: int = 512):
+    """train_util.py:407-419: a random multiple of 64 in [bucket/2, bucket) per side."""
+    step = 64
+    min_step, max_step = (bucket_resolution // 2) // step, bucket_resolution // step
+    height = torch.randint(min_step, max_step, (1,)).item() * step
+    width = torch.randint(min_step, max_step, (1,)).item() * step
+    return height, width
+
+
+def get_optimizer(name: str):
+    """train_util.py:336-373.  `adamw` (the shipped configs' optimizer) is the fused sb200 AdamW, whose update is
+    bit-identical to torch.optim.AdamW on bf16 parameters; `adam` stays torch's.  The optional third-party optimizers
+    of the reference (dadaptation, bitsandbytes, lion_pytorch, prodigyopt) are not in this image."""
+    name = name.lower()
+    if name == "adamw":
+        from .optim import AdamW
+
+        return AdamW
+    if name == "adam":
+        return torch.optim.Adam
+    raise ValueError("Optimizer must be adam or adamw (dadapt* / *8bit / lion / prodigy need packages that are "
+                     "not installed here)")
+
+
+def get_lr_scheduler(name: Optional[str], optimizer: torch.optim.Optimizer, max_iterations: Optional[int],
+                     lr_min: Optional[float], **kwargs):
+    """train_util.py:376-404 (torch schedulers, unchanged)."""
+    sched = torch.optim.lr_scheduler
+    if name == "cosine":
+        return sched.CosineAnnealingLR(optimizer, T_max=max_iterations, eta_min=lr_min, **kwargs)
+    if name == "cosine_with_restarts":
+        return sched.CosineAnnealingWarmRestarts(optimizer, T_0=max_iterations // 10, T_mult=2, eta_min=lr_min, **kwargs)
+    if name == "step":
+        return sched.StepLR(optimizer, step_size=max_iterations // 100, gamma=0.999, **kwargs)
+    if name == "constant":
+        return sched.ConstantLR(optimizer, factor=1, **kwargs)
+    if name == "linear":
+        # the reference passes `factor=0.5`, which torch's LinearLR does not accept (TypeError at :399-402);
+        # `start_factor` is what that call means
+        return sched.LinearLR(optimizer, start_factor=0.5, total_iters=max_iterations // 100, **kwargs)
+    raise ValueError("Scheduler must be cosine, cosine_with_restarts, step, linear or constant")

@@ -1,0 +1,201 @@
+"""One optimisation step of the reference trainers, with the UNet forward / backward in sliders_b200 kernels:
+
+  text_slider_step_xl   trainscripts/textsliders/train_lora_xl.py:162-356   
+  text_slider_step      trainscripts/textsliders/train_lora.py:155-309      (SD1.x)
+  image_slider_step_xl  trainscripts/imagesliders/train_lora-scale-xl.py:178-384 (a9; latents in place of VAE-encoded
+                        image pairs — the VAE and the text encoders are off the denoise path)
+
+Prompt embeddings are inputs (the text encoders run once, before the loop: train_lora_xl.py:100-151).  The dataflow,
+the order of the UNet calls, where `with network:` is open, what carries grad, and the DDIM bookkeeping
+(`set_timesteps(max_denoising_steps)` -> partial denoise -> `set_timesteps(1000)` -> `current_timestep`) follow the
+reference line by line; `flush()` (gc + empty_cache, :356) is deliberately not replicated — the caching allocator
+keeping its blocks is what makes the next iteration launch-bound rather than malloc-bound.
+The two unused predictions of the image-slider loop (`high_latents`, `low_latents`, dead code in the reference,
+SURVEY.md §8 a9) are skipped unless `reference_dead_code=True`.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import train_util
+
+
+@dataclass
+class PromptEmbedsXL:
+    """prompt_util.py:28-35 — (text_embeds [1,77,2048], pooled_embeds [1,1280])."""
+    text_embeds: torch.Tensor
+    pooled_embeds: torch.Tensor
+
+
+@dataclass
+class PromptSettings:
+    """prompt_util.py:38-68 (fields used inside the training loop)."""
+    guidance_scale: float = 1.0
+    resolution: int = 512
+    dynamic_resolution: bool = False
+    batch_size: int = 1
+    dynamic_crops: bool = False
+    action: str = "erase"
+
+
+class PromptEmbedsPair:
+    """prompt_util.py:71-148: the four embeddings of one slider prompt plus the erase / enhance objective."""
+
+    def __init__(self, loss_fn, target, positive, unconditional, neutral, settings: PromptSettings):
+        self.loss_fn = loss_fn
+        self.target, self.positive, self.unconditional, self.neutral = target, positive, unconditional, neutral
+        self.guidance_scale = settings.guidance_scale
+        self.resolution = settings.resolution
+        self.dynamic_resolution = settings.dynamic_resolution
+        self.batch_size = settings.batch_size
+        self.dynamic_crops = settings.dynamic_crops
+        self.action = settings.action
+
+    def loss(self, target_latents, positive_latents, unconditional_latents, neutral_latents):
+        if self.action == "erase":      # prompt_util.py:108-121
+            return self.loss_fn(target_latents,
+                                neutral_latents - self.guidance_scale * (positive_latents - unconditional_latents))
+        if self.action == "enhance":    # :123-135
+            return self.loss_fn(target_latents,
+                                neutral_latents + self.guidance_scale * (positive_latents - unconditional_latents))
+        raise ValueError("action must be erase or enhance")
+
+
+def _xl_inputs(pair: PromptEmbedsPair, which: PromptEmbedsXL, add_time_ids):
+    bs = pair.batch_size
+    return dict(
+        text_embeddings=train_util.concat_embeddings(pair.unconditional.text_embeds, which.text_embeds, bs),
+        add_text_embeddings=train_util.concat_embeddings(pair.unconditional.pooled_embeds, which.pooled_embeds, bs),
+        add_time_ids=train_util.concat_embeddings(add_time_ids, add_time_ids, bs))
+
+
+def text_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler, prompt_pair: PromptEmbedsPair, *,
+                        max_denoising_steps: int = 50, timesteps_to: Optional[int] = None, device=None,
+                        weight_dtype=torch.bfloat16, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """train_lora_xl.py:162-347.  Returns the (detached) loss."""
+    device = device or unet.device
+    with torch.no_grad():
+        noise_scheduler.set_timesteps(max_denoising_steps, device=device)
+        optimizer.zero_grad()
+        if timesteps_to is None:
+            timesteps_to = torch.randint(1, max_denoising_steps, (1,)).item()          # :177-179
+        height = width = prompt_pair.resolution
+        if prompt_pair.dynamic_resolution:
+            height, width = train_util.get_random_resolution_in_bucket(prompt_pair.resolution)
+        latents = train_util.get_initial_latents(noise_scheduler, prompt_pair.batch_size, height, width, 1,
+                                                 generator=generator).to(device, dtype=weight_dtype)
+        add_time_ids = train_util.get_add_time_ids(height, width, dynamic_crops=prompt_pair.dynamic_crops,
+                                                   dtype=weight_dtype).to(device, dtype=weight_dtype)
+        with network:                                                                   # :205-227
+            denoised_latents = train_util.diffusion_xl(
+                unet, noise_scheduler, latents, **_xl_inputs(prompt_pair, prompt_pair.target, add_time_ids),
+                start_timesteps=0, total_timesteps=timesteps_to, guidance_scale=3)
+        noise_scheduler.set_timesteps(1000)
+        current_timestep = noise_scheduler.timesteps[int(timesteps_to * 1000 / max_denoising_steps)]
+        # outside `with network:` the adaptors are inert (:236-297)
+        preds = {}
+        for name in ("positive", "neutral", "unconditional"):
+            preds[name] = train_util.predict_noise_xl(
+                unet, noise_scheduler, current_timestep, denoised_latents,
+                **_xl_inputs(prompt_pair, getattr(prompt_pair, name), add_time_ids),
+                guidance_scale=1).to(device, dtype=weight_dtype)
+    with network:                                                                       # :299-322, grad on
+        target_latents = train_util.predict_noise_xl(
+            unet, noise_scheduler, current_timestep, denoised_latents,
+            **_xl_inputs(prompt_pair, prompt_pair.target, add_time_ids), guidance_scale=1).to(device, dtype=weight_dtype)
+    loss = prompt_pair.loss(target_latents=target_latents, positive_latents=preds["positive"],
+                            neutral_latents=preds["neutral"], unconditional_latents=preds["unconditional"])
+    loss.backward()                                                                     # :345
+    optimizer.step()
+    if lr_scheduler is not None:
+        lr_scheduler.step()
+    return loss.detach()
+
+
+def text_slider_step(unet, network, noise_scheduler, optimizer, lr_scheduler, prompt_pair: PromptEmbedsPair, *,
+                     max_denoising_steps: int = 50, timesteps_to: Optional[int] = None, device=None,
+                     weight_dtype=torch.bfloat16, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """train_lora.py:155-300 (SD1.x: embeddings are plain tensors [1,77,768], no added conditioning)."""
+    device = device or unet.device
+    bs = prompt_pair.batch_size
+    emb = lambda which: train_util.concat_embeddings(prompt_pair.unconditional, which, bs)
+    with torch.no_grad():
+        noise_scheduler.set_timesteps(max_denoising_steps, device=device)
+        optimizer.zero_grad()
+        if timesteps_to is None:
+            timesteps_to = torch.randint(1, max_denoising_steps, (1,)).item()
+        height = width = prompt_pair.resolution
+        latents = train_util.get_initial_latents(noise_scheduler, bs, height, width, 1,
+                                                 generator=generator).to(device, dtype=weight_dtype)
+        with network:
+            denoised_latents = train_util.diffusion(unet, noise_scheduler, latents, emb(prompt_pair.target),
+                                                    start_timesteps=0, total_timesteps=timesteps_to, guidance_scale=3)
+        noise_scheduler.set_timesteps(1000)
+        current_timestep = noise_scheduler.timesteps[int(timesteps_to * 1000 / max_denoising_steps)]
+        preds = {name: train_util.predict_noise(unet, noise_scheduler, current_timestep, denoised_latents,
+                                                emb(getattr(prompt_pair, name)), guidance_scale=1
+                                                ).to(device, dtype=weight_dtype)
+                 for name in ("positive", "neutral", "unconditional")}
+    with network:
+        target_latents = train_util.predict_noise(unet, noise_scheduler, current_timestep, denoised_latents,
+                                                  emb(prompt_pair.target), guidance_scale=1
+                                                  ).to(device, dtype=weight_dtype)
+    loss = prompt_pair.loss(target_latents=target_latents, positive_latents=preds["positive"],
+                            neutral_latents=preds["neutral"], unconditional_latents=preds["unconditional"])
+    loss.backward()
+    optimizer.step()
+    if lr_scheduler is not None:
+        lr_scheduler.step()
+    return loss.detach()
+
+
+def image_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler, prompt_pair: PromptEmbedsPair,
+                         latents_low: torch.Tensor, latents_high: torch.Tensor, scale_to_look: float, *,
+                         max_denoising_steps: int = 50, timesteps_to: Optional[int] = None, device=None,
+                         weight_dtype=torch.bfloat16, seed: Optional[int] = None,
+                         reference_dead_code: bool = False):
+    """train_lora-scale-xl.py:178-375 with the image pair already in latent space ([bs,4,h,w], scaled by the VAE
+    factor as `get_noisy_image` does, imagesliders/train_util.py:201-235).  Two grad-carrying predictions (+scale on
+    the `high` sample, -scale on the `low` one), two `backward()` calls accumulating into .grad, one optimizer step."""
+    device = device or unet.device
+    criteria = torch.nn.MSELoss()
+    with torch.no_grad():
+        noise_scheduler.set_timesteps(max_denoising_steps, device=device)
+        optimizer.zero_grad()
+        if timesteps_to is None:
+            timesteps_to = torch.randint(1, max_denoising_steps - 1, (1,)).item()       # :193-196
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 15, (1,)).item())
+        h, w = latents_low.shape[-2:]
+        height, width = h * train_util.VAE_SCALE_FACTOR, w * train_util.VAE_SCALE_FACTOR
+        timestep = noise_scheduler.timesteps[timesteps_to]                              # get_noisy_image :224-231
+        noise = torch.randn(latents_low.shape, generator=torch.Generator().manual_seed(seed)).to(device)
+        ts = torch.as_tensor(timestep).reshape(1)
+        noisy_low = noise_scheduler.add_noise(latents_low.to(device).float(), noise, ts).to(weight_dtype)
+        noisy_high = noise_scheduler.add_noise(latents_high.to(device).float(), noise, ts).to(weight_dtype)
+        noise_scheduler.set_timesteps(1000)
+        add_time_ids = train_util.get_add_time_ids(height, width, dynamic_crops=prompt_pair.dynamic_crops,
+                                                   dtype=weight_dtype).to(device, dtype=weight_dtype)
+        current_timestep = noise_scheduler.timesteps[int(timesteps_to * 1000 / max_denoising_steps)]
+        if reference_dead_code:  # :258-306, results unused by the loss
+            train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy_high,
+                                        **_xl_inputs(prompt_pair, prompt_pair.positive, add_time_ids), guidance_scale=1)
+            train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy_low,
+                                        **_xl_inputs(prompt_pair, prompt_pair.neutral, add_time_ids), guidance_scale=1)
+    losses = []
+    for sign, noisy, which in ((+1.0, noisy_high, prompt_pair.positive), (-1.0, noisy_low, prompt_pair.neutral)):
+        network.set_lora_slider(scale=sign * scale_to_look)                             # :311, :343
+        with network:
+            pred = train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy,
+                                               **_xl_inputs(prompt_pair, which, add_time_ids),
+                                               guidance_scale=1).to(device, dtype=torch.float32)
+        loss = criteria(pred, noise.to(torch.float32))                                  # :338, :370
+        loss.backward()
+        losses.append(loss.detach())
+    optimizer.step()
+    if lr_scheduler is not None:
+        lr_scheduler.step()
+    return losses

@@ -579,11 +579,14 @@ class UNet2DConditionModel(nn.Module):
     # ---- public forward --------------------------------------------------------------------------------
     def forward(self, sample, timestep, encoder_hidden_states=None, added_cond_kwargs=None,
                 cross_attention_kwargs=None, return_dict: bool = True, **unused):
-        self._check_no_grad_needed()
+        if torch.is_grad_enabled() and self._needs_grad():
+            # training: keep activations and hand torch.autograd a node whose backward runs the sb200 backward kernels
+            return self._forward_nograd(sample, timestep, encoder_hidden_states, added_cond_kwargs, return_dict,
+                                        train=True)
         with torch.no_grad():
             return self._forward_nograd(sample, timestep, encoder_hidden_states, added_cond_kwargs, return_dict)
 
-    def _forward_nograd(self, sample, timestep, encoder_hidden_states, added_cond_kwargs, return_dict):
+    def _forward_nograd(self, sample, timestep, encoder_hidden_states, added_cond_kwargs, return_dict, train=False):
         if not sample.is_cuda:
             raise RuntimeError("sliders_b200.UNet2DConditionModel runs only on a CUDA (sm_100) device; "
                                "there is no CPU path (the CPU oracle lives under oracle/ for tests)")
@@ -600,7 +603,11 @@ class UNet2DConditionModel(nn.Module):
         x = sample if sample.dtype in (torch.float32, BF16) else sample.to(BF16)
         x = x.contiguous()
         ehs = encoder_hidden_states.to(device=dev, dtype=BF16).contiguous()
-        if self.use_cuda_graph:
+        if train:
+            from . import autograd as sb_autograd
+
+            out = sb_autograd.apply(self, x.detach(), t, ehs.detach(), added_cond_kwargs, out_dtype)
+        elif self.use_cuda_graph:
             out = self._graphed(x, t, ehs, added_cond_kwargs, out_dtype)
         else:
             out = self._forward_impl(x, t, ehs, added_cond_kwargs, out_dtype)
@@ -629,14 +636,12 @@ class UNet2DConditionModel(nn.Module):
             return (tuple(s != 0.0 for s in scales), None), nz[0]
         return (tuple(s != 0.0 for s in scales), tuple(scales)), None
 
-    def _check_no_grad_needed(self):
-        if not torch.is_grad_enabled():
-            return
+    def _needs_grad(self) -> bool:
+        """True when an active adaptor (multiplier != 0, i.e. inside `with network:`) has trainable weights."""
         for _, a in self._adapted_leaves():
-            if float(a.multiplier) != 0.0 and a.lora_down.weight.requires_grad:
-                raise NotImplementedError(
-                    "sliders_b200 round 1 implements the forward (denoise / inference) path only; the "
-                    "backward-to-LoRA kernels are SURVEY.md §8(f) rank 1.  Call under torch.no_grad().")
+            if float(a.multiplier) * float(a.scale) != 0.0 and a.lora_down.weight.requires_grad:
+                return True
+        return False
 
     def _graphed(self, x, t, ehs, added, out_dtype):
         sig, _ = self._lora_signature()

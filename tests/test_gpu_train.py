@@ -1,0 +1,97 @@
+"""End-to-end optimisation steps of the three trainers (sliders_b200/trainer.py) on the tiny fixtures' models:
+the text-slider step (train_lora_xl.py:162-356 / train_lora.py:155-309) and the image-slider step
+(train_lora-scale-xl.py:178-384), forward and backward in sb200 kernels, AdamW fused."""
+import os
+
+import pytest
+import torch
+
+from test_gpu_unet import GOLDEN, build_product, dev  # noqa: F401  (fixture re-export)
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _xl_pair(trainer, fx, d, action="enhance", bs=1):
+    g = torch.Generator().manual_seed(7)
+    mk = lambda: trainer.PromptEmbedsXL(torch.randn(1, 77, 256, generator=g).to(d, BF),
+                                        torch.randn(1, 128, generator=g).to(d, BF))
+    unc, tgt, pos = mk(), mk(), mk()
+    st = trainer.PromptSettings(guidance_scale=4.0, resolution=256, batch_size=bs, action=action)
+    return trainer.PromptEmbedsPair(torch.nn.MSELoss(), tgt, pos, unc, unc, st)
+
+
+def test_text_slider_steps_xl(dev):
+    from sliders_b200 import trainer, train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+
+    fx = torch.load(os.path.join(GOLDEN, "tiny_xl.pt"))
+    pm, net = build_product(fx, dev)
+    net.requires_grad_(True)
+    params = net.prepare_optimizer_params()
+    opt = train_util.get_optimizer("AdamW")(params, lr=2e-3)
+    lr_sched = train_util.get_lr_scheduler("constant", opt, 100, 1e-6)
+    sched = create_noise_scheduler("ddim")
+    pair = _xl_pair(trainer, fx, dev)
+    before = {k: v.detach().clone() for k, v in net.named_parameters()}
+    gen = torch.Generator().manual_seed(3)
+    losses = []
+    for it in range(6):
+        gen.manual_seed(3)  # same initial noise / same timestep: the loss must go down as the slider learns it
+        losses.append(float(trainer.text_slider_step_xl(pm, net, sched, opt, lr_sched, pair, max_denoising_steps=50,
+                                                        timesteps_to=2, device=dev, weight_dtype=BF, generator=gen)))
+    assert all(l == l and l < 1e4 for l in losses)
+    assert losses[-1] < losses[0], losses
+    changed = sum(int(not torch.equal(before[k], v.detach())) for k, v in net.named_parameters())
+    assert changed == len(before)
+    assert all(float(l.multiplier) == 0.0 for l in net.unet_loras)  # `with network:` closed (lora.py:256-258)
+    # erase action, random timestep, batch 2
+    pair2 = _xl_pair(trainer, fx, dev, action="erase", bs=2)
+    l = trainer.text_slider_step_xl(pm, net, sched, opt, lr_sched, pair2, device=dev, weight_dtype=BF)
+    assert torch.isfinite(l)
+
+
+def test_text_slider_step_sd(dev):
+    from sliders_b200 import trainer, train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+
+    fx = torch.load(os.path.join(GOLDEN, "tiny_sd.pt"))
+    pm, net = build_product(fx, dev)
+    net.requires_grad_(True)
+    opt = train_util.get_optimizer("AdamW")(net.prepare_optimizer_params(), lr=1e-3)
+    sched = create_noise_scheduler("ddim")
+    g = torch.Generator().manual_seed(5)
+    D = fx["text_embeddings"].shape[-1]
+    unc, tgt, pos = (torch.randn(1, 77, D, generator=g).to(dev, BF) for _ in range(3))
+    st = trainer.PromptSettings(guidance_scale=1.0, resolution=256, batch_size=1, action="erase")
+    pair = trainer.PromptEmbedsPair(torch.nn.MSELoss(), tgt, pos, unc, unc, st)
+    gen = torch.Generator()
+    losses = []
+    for _ in range(4):
+        gen.manual_seed(1)
+        losses.append(float(trainer.text_slider_step(pm, net, sched, opt, None, pair, timesteps_to=3, device=dev,
+                                                     weight_dtype=BF, generator=gen)))
+    assert losses[-1] < losses[0], losses
+
+
+def test_image_slider_step_xl(dev):
+    from sliders_b200 import trainer, train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+
+    fx = torch.load(os.path.join(GOLDEN, "tiny_xl.pt"))
+    pm, net = build_product(fx, dev)
+    net.requires_grad_(True)
+    opt = train_util.get_optimizer("AdamW")(net.prepare_optimizer_params(), lr=1e-3)
+    sched = create_noise_scheduler("ddim")
+    pair = _xl_pair(trainer, fx, dev)
+    g = torch.Generator().manual_seed(9)
+    low = torch.randn(1, 4, 32, 32, generator=g).to(dev)
+    high = low + 0.3 * torch.randn(1, 4, 32, 32, generator=g).to(dev)
+    first = last = None
+    for _ in range(4):
+        ls = trainer.image_slider_step_xl(pm, net, sched, opt, None, pair, low, high, 2.0, timesteps_to=20, seed=4,
+                                          device=dev, weight_dtype=BF)
+        tot = float(ls[0] + ls[1])
+        first = tot if first is None else first
+        last = tot
+    assert last < first, (first, last)

@@ -234,3 +234,53 @@ def test_launch_plan_dry_run_counts_and_flops():
     assert int(n) == 1008
     per_pass = float(flops) / 2
     assert abs(per_pass - 6.761e12) / 6.761e12 < 0.01, per_pass
+
+
+# ---------------------------------------------------------------------------------------- trainer host logic
+def test_prompt_pair_loss_and_optimizer_factory():
+    from sliders_b200 import trainer, train_util
+    from sliders_b200.optim import AdamW
+
+    g = torch.Generator().manual_seed(0)
+    t, p, u, n = (torch.randn(1, 4, 8, 8, generator=g) for _ in range(4))
+    mse = torch.nn.MSELoss()
+    for action, sign in (("erase", -1.0), ("enhance", 1.0)):
+        pair = trainer.PromptEmbedsPair(mse, None, None, None, None,
+                                        trainer.PromptSettings(guidance_scale=4.0, action=action))
+        got = pair.loss(target_latents=t, positive_latents=p, unconditional_latents=u, neutral_latents=n)
+        assert torch.allclose(got, mse(t, n + sign * 4.0 * (p - u)))
+    with pytest.raises(ValueError):
+        trainer.PromptEmbedsPair(mse, None, None, None, None, trainer.PromptSettings(action="x")).loss(
+            target_latents=t, positive_latents=p, unconditional_latents=u, neutral_latents=n)
+    assert train_util.get_optimizer("AdamW") is AdamW and train_util.get_optimizer("adam") is torch.optim.Adam
+    with pytest.raises(ValueError):
+        train_util.get_optimizer("lion")
+    for _ in range(20):
+        h, w = train_util.get_random_resolution_in_bucket(1024)
+        assert h % 64 == 0 and w % 64 == 0 and 512 <= h < 1024 and 512 <= w < 1024
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    for name in ("cosine", "cosine_with_restarts", "step", "constant", "linear"):
+        assert train_util.get_lr_scheduler(name, opt, 1000, 1e-6) is not None
+    with pytest.raises(ValueError):
+        train_util.get_lr_scheduler("nope", opt, 1000, 1e-6)
+
+
+def test_reference_prompt_pair_loss_matches_ours():
+    from oracle import reference_bridge as rb
+
+    if not rb.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from sliders_b200 import trainer
+
+    pu = rb.load("prompt_util")
+    g = torch.Generator().manual_seed(1)
+    t, p, u, n = (torch.randn(2, 4, 8, 8, generator=g) for _ in range(4))
+    for action in ("erase", "enhance"):
+        rs = pu.PromptSettings(target="t", positive="p", unconditional="u", neutral="n", action=action,
+                               guidance_scale=2.5, resolution=512, batch_size=2)
+        ref = pu.PromptEmbedsPair(torch.nn.MSELoss(), None, None, None, None, rs)
+        ours = trainer.PromptEmbedsPair(torch.nn.MSELoss(), None, None, None, None,
+                                        trainer.PromptSettings(guidance_scale=2.5, action=action, batch_size=2))
+        kw = dict(target_latents=t, positive_latents=p, unconditional_latents=u, neutral_latents=n)
+        assert torch.equal(ref.loss(**kw), ours.loss(**kw))
+        assert (ref.batch_size, ref.resolution, ref.dynamic_crops) == (ours.batch_size, 512, ours.dynamic_crops)
