@@ -29,7 +29,9 @@ def denoise_loop(unet, network, scheduler, latents: torch.Tensor, prompt_embeds:
     added = None
     if add_text_embeds is not None:
         added = {"text_embeds": add_text_embeds, "time_ids": add_time_ids}
-    for i, t in enumerate(scheduler.timesteps):
+    # host-side timestep values: `int(t)` on a CUDA scalar would synchronise the device once per step
+    steps = getattr(scheduler, "timesteps_host", None) or scheduler.timesteps
+    for i, t in enumerate(steps):
         # generate_images_xl.py:327-330
         network.set_lora_slider(scale=0 if int(t) > start_noise else scale)
         x = scheduler.scale_model_input(torch.cat([latents] * 2), t)

@@ -55,4 +55,9 @@ class AdamW(torch.optim.Optimizer):
             table = torch.tensor([r[:5] for r in rows], dtype=torch.int64).to(dev, non_blocking=False)
             b1, b2 = group["betas"]
             ops.adamw(table, len(rows), max_n, group["lr"], b1, b2, group["eps"], group["weight_decay"], steps.pop())
+            # the kernel wrote the parameters behind torch's back: bump their version counters so that consumers
+            # keyed on `_version` (the packed-LoRA cache in unet._lora, autograd's saved-tensor checks) see the update
+            for p in group["params"]:
+                if p.grad is not None:
+                    torch.autograd.graph.increment_version(p)
         return loss

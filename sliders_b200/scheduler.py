@@ -63,6 +63,9 @@ class DDIMScheduler:
         ts = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
         ts += self.config.steps_offset
         self.timesteps = torch.from_numpy(ts).to(device)
+        # host mirror: the denoise loops index it so that no step has to read a CUDA scalar back (a device sync per
+        # step; diffusers' scheduler.step does exactly that when `set_timesteps(..., device=cuda)` is used)
+        self.timesteps_host = [int(v) for v in ts]
 
     def _alphas_for(self, timestep) -> tuple:
         t = int(timestep)

@@ -71,7 +71,9 @@ def predict_noise_xl(unet, scheduler, timestep, latents, text_embeddings, add_te
 
 
 def _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_scale, total_timesteps, start_timesteps):
-    for timestep in scheduler.timesteps[start_timesteps:total_timesteps]:
+    host = getattr(scheduler, "timesteps_host", None)
+    steps = host[start_timesteps:total_timesteps] if host is not None else scheduler.timesteps[start_timesteps:total_timesteps]
+    for timestep in steps:  # python ints: nothing in the loop reads the device back
         x = scheduler.scale_model_input(latents, timestep)
         noise_pred = _unet_pair(unet, x, timestep, text_embeddings, added)
         a_t, a_prev = scheduler._alphas_for(timestep)

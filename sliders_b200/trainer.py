@@ -20,7 +20,9 @@ from typing import Optional
 
 import torch
 
-from . import train_util
+import torch.distributed as dist
+
+from . import parallel, train_util
 
 
 @dataclass
@@ -64,6 +66,16 @@ class PromptEmbedsPair:
         raise ValueError("action must be erase or enhance")
 
 
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _global_rank(group_rank: int, group=None) -> int:
+    return dist.get_global_rank(group, group_rank) if group is not None else group_rank
+
+
 def _xl_inputs(pair: PromptEmbedsPair, which: PromptEmbedsXL, add_time_ids):
     bs = pair.batch_size
     return dict(
@@ -74,19 +86,31 @@ def _xl_inputs(pair: PromptEmbedsPair, which: PromptEmbedsXL, add_time_ids):
 
 def text_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler, prompt_pair: PromptEmbedsPair, *,
                         max_denoising_steps: int = 50, timesteps_to: Optional[int] = None, device=None,
-                        weight_dtype=torch.bfloat16, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-    """train_lora_xl.py:162-347.  Returns the (detached) loss."""
+                        weight_dtype=torch.bfloat16, generator: Optional[torch.Generator] = None,
+                        group=None) -> torch.Tensor:
+    """train_lora_xl.py:162-347.  Returns the (detached) loss.
+
+    Under torch.distributed (one process per GPU) the four conditioned predictions are sharded one per rank
+    (BASELINE config 3): the serial partial denoise runs replicated (same seed on every rank), the three frozen
+    predictions are broadcast to the rank that owns the grad-carrying `target` prediction, that rank back-propagates,
+    and ONE all-reduce of the flat LoRA gradient buffer makes every replica take the same AdamW step."""
     device = device or unet.device
     with torch.no_grad():
         noise_scheduler.set_timesteps(max_denoising_steps, device=device)
         optimizer.zero_grad()
         if timesteps_to is None:
             timesteps_to = torch.randint(1, max_denoising_steps, (1,)).item()          # :177-179
+            if _world(group)[0] > 1:  # every replica must pick the same step count
+                tt = torch.tensor([timesteps_to], device=device)
+                dist.broadcast(tt, src=_global_rank(0, group), group=group)
+                timesteps_to = int(tt.item())
         height = width = prompt_pair.resolution
         if prompt_pair.dynamic_resolution:
             height, width = train_util.get_random_resolution_in_bucket(prompt_pair.resolution)
         latents = train_util.get_initial_latents(noise_scheduler, prompt_pair.batch_size, height, width, 1,
                                                  generator=generator).to(device, dtype=weight_dtype)
+        if _world(group)[0] > 1:
+            dist.broadcast(latents, src=_global_rank(0, group), group=group)  # replicas denoise the same noise
         add_time_ids = train_util.get_add_time_ids(height, width, dynamic_crops=prompt_pair.dynamic_crops,
                                                    dtype=weight_dtype).to(device, dtype=weight_dtype)
         with network:                                                                   # :205-227
@@ -96,19 +120,36 @@ def text_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler,
         noise_scheduler.set_timesteps(1000)
         current_timestep = noise_scheduler.timesteps[int(timesteps_to * 1000 / max_denoising_steps)]
         # outside `with network:` the adaptors are inert (:236-297)
+        world, rank = _world(group)
+        owner = {name: i % world for i, name in enumerate(("positive", "neutral", "unconditional", "target"))}
         preds = {}
         for name in ("positive", "neutral", "unconditional"):
-            preds[name] = train_util.predict_noise_xl(
+            if owner[name] == rank:
+                preds[name] = train_util.predict_noise_xl(
+                    unet, noise_scheduler, current_timestep, denoised_latents,
+                    **_xl_inputs(prompt_pair, getattr(prompt_pair, name), add_time_ids),
+                    guidance_scale=1).to(device, dtype=weight_dtype)
+        if world > 1:  # one condition per GPU: the three frozen predictions travel to the target rank
+            for name in ("positive", "neutral", "unconditional"):
+                if owner[name] != rank:
+                    preds[name] = torch.empty_like(denoised_latents, dtype=weight_dtype)
+                dist.broadcast(preds[name], src=_global_rank(owner[name], group), group=group)
+    loss = torch.zeros((), device=device)
+    if owner["target"] == rank:
+        with network:                                                                   # :299-322, grad on
+            target_latents = train_util.predict_noise_xl(
                 unet, noise_scheduler, current_timestep, denoised_latents,
-                **_xl_inputs(prompt_pair, getattr(prompt_pair, name), add_time_ids),
+                **_xl_inputs(prompt_pair, prompt_pair.target, add_time_ids),
                 guidance_scale=1).to(device, dtype=weight_dtype)
-    with network:                                                                       # :299-322, grad on
-        target_latents = train_util.predict_noise_xl(
-            unet, noise_scheduler, current_timestep, denoised_latents,
-            **_xl_inputs(prompt_pair, prompt_pair.target, add_time_ids), guidance_scale=1).to(device, dtype=weight_dtype)
-    loss = prompt_pair.loss(target_latents=target_latents, positive_latents=preds["positive"],
-                            neutral_latents=preds["neutral"], unconditional_latents=preds["unconditional"])
-    loss.backward()                                                                     # :345
+        loss = prompt_pair.loss(target_latents=target_latents, positive_latents=preds["positive"],
+                                neutral_latents=preds["neutral"], unconditional_latents=preds["unconditional"])
+        loss.backward()                                                                 # :345
+    if world > 1:
+        # one all-reduce of the flat LoRA-gradient buffer (ranks without the graph contribute zeros), so every
+        # replica applies the identical optimizer step
+        parallel.allreduce_lora_grads([p for g in optimizer.param_groups for p in g["params"]], group=group)
+        loss = loss.detach().float().clone()
+        dist.broadcast(loss, src=_global_rank(owner["target"], group), group=group)
     optimizer.step()
     if lr_scheduler is not None:
         lr_scheduler.step()

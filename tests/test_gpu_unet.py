@@ -383,3 +383,76 @@ def test_full_sd15_parity_vs_fp32_oracle(dev):
         with net:
             got = train_util.predict_noise(pm, sched, 321, lat, ehs, guidance_scale=1.0)
     assert rel_rms(got, ref) < 2.5e-2
+
+
+def test_full_sdxl_lora_gradients_vs_fp32_oracle(dev):
+    """BASELINE-size backward: SDXL UNet, 128x128 latents, CFG pair, rank-4 LoRA on 346 leaves.  The oracle is the
+    fp32 restatement under torch autograd with W_eff = W + s * up @ down built from leaf tensors (the same function
+    as the reference's forward hook, tests/test_oracle.py pins that), so its d/d(up, down) are the reference's
+    gradients.  Tolerance: bf16 back-propagation through ~400 layers vs fp32 -> global rel-RMS <= 6e-2."""
+    from oracle import unet as ounet
+    from sliders_b200 import lora as plora, synthetic, train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    with torch.device(dev):
+        pm = UNet2DConditionModel(UNetConfig.sdxl()).to(BF)
+        om = ounet.UNet2DConditionModel(ounet.UNetConfig.sdxl())
+    synthetic.init_synthetic_(pm, seed=1)
+    om.load_state_dict({k: v.float() for k, v in pm.state_dict().items()})
+    om.eval().requires_grad_(False)
+    pm.requires_grad_(False)
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+    synthetic.init_lora_nonzero_(net, seed=2, up_std=0.05)
+    net.requires_grad_(True)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 4, 128, 128, generator=g).to(dev, BF)
+    ehs = torch.randn(2, 77, 2048, generator=g).to(dev, BF)
+    pooled = torch.randn(2, 1280, generator=g).to(dev, BF)
+    tids = torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]] * 2, device=dev)
+    goal = torch.randn(1, 4, 128, 128, generator=g).to(dev)
+    sched = create_noise_scheduler("ddim")
+    sched.set_timesteps(1000)
+    net.set_lora_slider(1.5)
+    with net:
+        pred = train_util.predict_noise_xl(pm, sched, 500, lat, ehs, pooled, tids, guidance_scale=1)
+    loss = torch.nn.functional.mse_loss(pred.float(), goal)
+    loss.backward()
+    torch.cuda.synchronize()
+    # ---- oracle
+    names = {"lora_unet_" + n.replace(".", "_"): n for n, _ in om.named_modules()}
+    params = dict(om.named_parameters())
+    leaves, eff = {}, {}
+    for l in net.unet_loras:
+        down = l.lora_down.weight.detach().float().requires_grad_()
+        up = l.lora_up.weight.detach().float().requires_grad_()
+        leaves[l.lora_name] = (down, up)
+        w = params[names[l.lora_name] + ".weight"]
+        s = 1.5 * l.scale
+        if down.dim() == 4:
+            delta = torch.einsum("or,rikl->oikl", up[:, :, 0, 0], down)
+        else:
+            delta = up @ down
+        eff[names[l.lora_name] + ".weight"] = w + s * delta
+    full = {**params, **eff}
+    out = torch.func.functional_call(om, full, (torch.cat([lat.float()] * 2), 500, ehs.float()),
+                                     {"added_cond_kwargs": {"text_embeds": pooled.float(), "time_ids": tids}}).sample
+    u, c = out.chunk(2)
+    ref_pred = u + 1.0 * (c - u)
+    assert rel_rms(pred, ref_pred) < 2.5e-2
+    torch.nn.functional.mse_loss(ref_pred, goal).backward()
+    num = den = 0.0
+    worst = (0.0, None)
+    for l in net.unet_loras:
+        for got, ref in ((l.lora_down.weight.grad, leaves[l.lora_name][0].grad),
+                         (l.lora_up.weight.grad, leaves[l.lora_name][1].grad)):
+            assert got is not None and torch.isfinite(got).all(), l.lora_name
+            e, n = (got.float() - ref).pow(2).sum().item(), ref.pow(2).sum().item()
+            num, den = num + e, den + n
+            r = (e / max(n, 1e-30)) ** 0.5
+            if r > worst[0]:
+                worst = (r, l.lora_name)
+    total = (num / den) ** 0.5
+    print(f"SDXL LoRA gradient rel-RMS vs fp32 oracle: global {total:.4f}, worst tensor {worst[0]:.4f} ({worst[1]})")
+    assert total < 6e-2, (total, worst)

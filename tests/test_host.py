@@ -284,3 +284,81 @@ def test_reference_prompt_pair_loss_matches_ours():
         kw = dict(target_latents=t, positive_latents=p, unconditional_latents=u, neutral_latents=n)
         assert torch.equal(ref.loss(**kw), ours.loss(**kw))
         assert (ref.batch_size, ref.resolution, ref.dynamic_crops) == (ours.batch_size, 512, ours.dynamic_crops)
+
+
+_TRAIN_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sliders_b200 import trainer, train_util
+world = int(sys.argv[4])
+if world > 1:
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=world)
+
+# stand-ins for the UNet call sites (the kernels need a GPU): any differentiable function of the adaptor weights
+class Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(5)
+        self.a = torch.nn.Parameter(torch.randn(4, 4, generator=g) * 0.3)
+        self.b = torch.nn.Parameter(torch.randn(4, generator=g) * 0.3)
+        self.multiplier = 0.0
+    def __enter__(self): self.multiplier = 1.0
+    def __exit__(self, *a): self.multiplier = 0.0
+net = Net()
+calls = []
+def predict_noise_xl(unet, sched, t, lat, text_embeddings, add_text_embeddings, add_time_ids, guidance_scale=7.5, **kw):
+    calls.append("predict")
+    e = text_embeddings.mean() + add_text_embeddings.mean()
+    out = torch.tanh(lat.float() + e)
+    if net.multiplier:
+        out = out + net.multiplier * (torch.einsum("oc,bchw->bohw", net.a, lat.float()) + net.b[None, :, None, None])
+    return out
+def diffusion_xl(unet, sched, lat, text_embeddings, add_text_embeddings, add_time_ids, guidance_scale=1.0,
+                 total_timesteps=1000, start_timesteps=0):
+    calls.append("denoise")
+    return lat * 0.9 + 0.01 * total_timesteps
+train_util.predict_noise_xl, train_util.diffusion_xl = predict_noise_xl, diffusion_xl
+from sliders_b200.scheduler import create_noise_scheduler
+sched = create_noise_scheduler("ddim")
+g = torch.Generator().manual_seed(1)
+mk = lambda: trainer.PromptEmbedsXL(torch.randn(1, 77, 8, generator=g), torch.randn(1, 4, generator=g))
+unc, tgt, pos, neu = mk(), mk(), mk(), mk()
+pair = trainer.PromptEmbedsPair(torch.nn.MSELoss(), tgt, pos, unc, neu,
+                                trainer.PromptSettings(guidance_scale=2.0, resolution=64, batch_size=2, action="erase"))
+opt = torch.optim.AdamW(net.parameters(), lr=1e-2)
+losses = []
+for it in range(3):
+    gen = torch.Generator().manual_seed(100 + it + (dist.get_rank() if world > 1 else 0))  # ranks draw DIFFERENT noise
+    losses.append(float(trainer.text_slider_step_xl(None, net, sched, opt, None, pair, timesteps_to=None if it else 7,
+                                                    device="cpu", weight_dtype=torch.float32, generator=gen)))
+torch.save({"a": net.a.detach(), "b": net.b.detach(), "losses": losses, "calls": calls}, sys.argv[5])
+if world > 1:
+    dist.destroy_process_group()
+print("ok")
+'''
+
+
+def test_text_slider_step_sharded_two_ranks_gloo(tmp_path):
+    """BASELINE config 3's host logic on CPU: with the four predictions sharded over 2 ranks the replicas end with
+    identical adaptor weights, each rank runs only its share of the predictions, and rank 0's trajectory equals the
+    single-process one (rank 0's noise is broadcast)."""
+    script = tmp_path / "train_worker.py"
+    script.write_text(_TRAIN_WORKER)
+    port = 31500 + (os.getpid() % 2000)
+    outs = [str(tmp_path / f"out{r}.pt") for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), "2", outs[r]],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    logs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, logs):
+        assert p.returncode == 0 and "ok" in o, o
+    single = str(tmp_path / "single.pt")
+    p = subprocess.run([sys.executable, str(script), ROOT, str(port + 1), "0", "1", single], capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    r0, r1, s = torch.load(outs[0]), torch.load(outs[1]), torch.load(single)
+    assert torch.equal(r0["a"], r1["a"]) and torch.equal(r0["b"], r1["b"])
+    assert r0["losses"] == r1["losses"]
+    # iteration 0 has a fixed step count and rank 0's noise: same loss as the single process
+    assert abs(r0["losses"][0] - s["losses"][0]) < 1e-6
+    assert r0["calls"].count("predict") == 6 and r1["calls"].count("predict") == 6  # 2 of the 4 predictions each
+    assert s["calls"].count("predict") == 12
