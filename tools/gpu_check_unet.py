@@ -170,8 +170,9 @@ if __name__ == "__main__":
         # one eager forward of 8 passes between cudaProfilerStart/Stop (run under `ncu --profile-from-start off`)
         sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         import bench
-        unet, net = bench.build_product(dev, 8)
-        lat_h, ehs_h, pooled_h, tids_h = bench.make_host_inputs(8, pin=False)
+        nb = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+        unet, net = bench.build_product(dev, nb)
+        lat_h, ehs_h, pooled_h, tids_h = bench.make_host_inputs(nb, pin=False)
         args = (lat_h.to(dev), 500, ehs_h.to(dev))
         added = {"text_embeds": pooled_h.to(dev), "time_ids": tids_h.to(dev)}
         with torch.no_grad(), net:

@@ -93,7 +93,7 @@ def main():
               f"loss {float(loss):.5f}")
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "prof"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("prof", "ncu")):
     main()
 
 
@@ -145,3 +145,40 @@ def profile_iteration():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "prof":
     profile_iteration()
+
+
+def ncu_mode():
+    """One training forward + backward (SDXL CFG pair) between cudaProfilerStart/Stop:
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv ... python tools/gpu_time_train.py ncu"""
+    dev = torch.device("cuda:0")
+    with torch.device(dev):
+        pm = UNet2DConditionModel(UNetConfig.sdxl()).to(BF)
+    synthetic.init_synthetic_(pm, seed=1)
+    pm.requires_grad_(False)
+    saved = list(plora.DEFAULT_TARGET_REPLACE)
+    plora.DEFAULT_TARGET_REPLACE += plora.UNET_TARGET_REPLACE_MODULE_CONV
+    net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+    del plora.DEFAULT_TARGET_REPLACE[len(saved):]
+    synthetic.init_lora_nonzero_(net, seed=2, up_std=0.02)
+    net.requires_grad_(True)
+    sched = create_noise_scheduler("ddim")
+    sched.set_timesteps(1000)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 4, 128, 128, generator=g).to(dev, BF)
+    ehs = torch.randn(2, 77, 2048, generator=g).to(dev, BF)
+    pooled = torch.randn(2, 1280, generator=g).to(dev, BF)
+    tids = train_util.get_add_time_ids(1024, 1024, dtype=BF).to(dev).repeat(2, 1)
+    goal = torch.randn(1, 4, 128, 128, generator=g).to(dev, BF)
+    for rep in range(2):
+        if rep == 1:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+        with net:
+            pred = train_util.predict_noise_xl(pm, sched, 500, lat, ehs, pooled, tids, guidance_scale=1)
+        torch.nn.functional.mse_loss(pred, goal).backward()
+        torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ncu":
+    ncu_mode()
