@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=25.0)
+    ap.add_argument("--no-train", action="store_true", help="skip the text-slider training-iteration timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -314,9 +315,22 @@ def main():
     gemm_n = per_kind.get("gemm", [0, 0, 0])[2] + per_kind.get("conv3x3", [0, 0, 0])[2]
     total_ms_eager = sum(v[0] for v in per_kind.values())
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel: from the committed ncu capture of the same workload (profiles/), per launch
+    traffic, traffic_note = None, None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_b8.json")) as f:
+            dj = json.load(f)["per_kernel"]["gemm_kernel"]
+        if B == 8:
+            traffic = dj["dram_read_bytes_per_launch"] + dj["dram_write_bytes_per_launch"]
+            traffic_note = ("bytes per gemm_kernel launch (mean over the 493 launches of one 8-pass forward), ncu "
+                            "dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_dram_b8_ncu.csv; algorithmic "
+                            "A + W + out (+ residual) bytes per launch: 105.5e6")
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 GEMM / implicit-GEMM conv)",
                 "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["sustained"], "traffic": None, "peak_source": peaks["source"],
+                "frac": achieved / peaks["sustained"], "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": peaks["source"],
                 "launches": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
                 "share_of_step": gemm_ms / total_ms_eager if total_ms_eager else None,
                 "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(per_kind.items())},
@@ -388,6 +402,51 @@ def main():
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
            "api": "sliders_b200.train_util.predict_noise_xl (CFG pair, guidance 3) with pinned host buffers"}
     net.__exit__(None, None, None)
+
+    # ---- training path: whole text-slider iterations (train_lora_xl.py:162-356) through sliders_b200.trainer —
+    # partial denoise (25 of 50 DDIM steps, CFG pair, graph replays) + 3 frozen predictions + the grad-carrying one +
+    # backward-to-LoRA + fused AdamW.  Under torchrun the four predictions are sharded one per rank (BASELINE config 3).
+    train = None
+    if not args.no_train:
+        from sliders_b200 import trainer
+        net.requires_grad_(True)
+        opt = train_util.get_optimizer("AdamW")(net.prepare_optimizer_params(), lr=2e-4)
+        gtr = torch.Generator().manual_seed(77)
+        mk = lambda: trainer.PromptEmbedsXL(torch.randn(1, 77, 2048, generator=gtr).to(dev, torch.bfloat16),
+                                            torch.randn(1, 1280, generator=gtr).to(dev, torch.bfloat16))
+        unc, tgt, pos = mk(), mk(), mk()
+        pair = trainer.PromptEmbedsPair(torch.nn.MSELoss(), tgt, pos, unc, unc,
+                                        trainer.PromptSettings(guidance_scale=4.0, resolution=1024, batch_size=1,
+                                                               action="enhance"))
+        tsched = create_noise_scheduler("ddim")
+        n_it = 2
+        ops.launch_count = 0
+        for it in range(1 + n_it):
+            if it == 1:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                ops.launch_count = 0
+                e0.record()
+            loss = trainer.text_slider_step_xl(unet, net, tsched, opt, None, pair, timesteps_to=25, device=dev,
+                                               weight_dtype=torch.bfloat16,
+                                               generator=torch.Generator().manual_seed(1000 + it))
+        e1.record()
+        torch.cuda.synchronize()
+        t3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        it_ms = t3.item() / n_it
+        passes = 2 * (25 + 4)  # CFG pairs: 25 denoise steps + positive / neutral / unconditional / target
+        train = {"what": "text-slider iteration, SDXL 1024 px, batch 1, rank-4 LoRA (train_lora_xl.py:162-356): 25 DDIM "
+                         "denoise steps (guidance 3) + 4 CFG-pair predictions + backward-to-LoRA + AdamW(692 tensors)",
+                 "ms_per_iteration": it_ms, "iterations_timed": n_it, "passes_per_iteration": passes,
+                 "passes_per_s": passes / (it_ms * 1e-3), "loss": float(loss),
+                 "eager_launches_per_iteration": ops.launch_count // n_it,
+                 "sharding": ("single GPU" if world == 1 else
+                              f"4 predictions over ranks 0..{min(world, 4) - 1}, denoise replicated, 1 LoRA-grad all-reduce")}
+        net.requires_grad_(False)
+        opt = None
     unet.use_cuda_graph = False
 
     # ---- CPU baseline (rank 0, N == 1 only)
@@ -417,7 +476,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_fwd * args.steps,
-                "launches_per_step": launches_per_fwd, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "launches_per_step": launches_per_fwd, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "train": train}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
