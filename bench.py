@@ -444,7 +444,8 @@ def main():
                  "passes_per_s": passes / (it_ms * 1e-3), "loss": float(loss),
                  "eager_launches_per_iteration": ops.launch_count // n_it,
                  "sharding": ("single GPU" if world == 1 else
-                              f"4 predictions over ranks 0..{min(world, 4) - 1}, denoise replicated, 1 LoRA-grad all-reduce")}
+                              f"denoise CFG-split over rank parity (1 all-gather of 64 KiB per step), target prediction on rank "
+                              f"{world - 1}, frozen predictions over ranks 0..{max(world - 2, 0)}, 1 LoRA-grad all-reduce")}
         net.requires_grad_(False)
         opt = None
     unet.use_cuda_graph = False

@@ -59,21 +59,38 @@ def fanout_predict(predict: Callable[..., torch.Tensor], batch_args: Sequence[to
 
 
 def allreduce_lora_grads(params: Sequence[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None) -> None:
-    """Sum LoRA gradients over ranks with ONE collective on a flat buffer (ranks that held no graph contribute
-    zeros), then scatter the result back into the .grad views."""
+    """Sum LoRA gradients over ranks with ONE collective on a flat fp32 buffer (ranks that held no graph contribute
+    zeros); afterwards every `.grad` is a view of the reduced buffer (cast to the parameter dtype), so the whole
+    exchange is one concat, one all-reduce and one cast regardless of the number of tensors (692 at SDXL rank 4)."""
     if not dist.is_available() or not dist.is_initialized():
         return
     ps = [p for p in params if p.requires_grad]
     if not ps:
         return
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in ps])
+    dev = ps[0].device
+    if all(p.grad is None for p in ps):
+        flat = torch.zeros(sum(p.numel() for p in ps), device=dev, dtype=torch.float32)
+    else:
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps]).float()
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    by_dtype = {}
     off = 0
     for p in ps:
         n = p.numel()
-        g = flat[off:off + n].view_as(p).to(p.dtype)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
+        src = by_dtype.get(p.dtype)
+        if src is None:
+            src = by_dtype[p.dtype] = flat if p.dtype == torch.float32 else flat.to(p.dtype)
+        p.grad = src[off:off + n].view_as(p)
         off += n
+
+
+def cfg_split_eps(eps_half: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """CFG-split of a serial denoise step over two (or more) ranks: even ranks computed the unconditional half of the
+    CFG pair, odd ranks the conditional half; one all-gather (64 KiB per sample at 1024 px) gives every rank
+    [uncond ; cond].  Ranks >= 2 duplicate the work of rank (rank % 2) — the loop is serial, there is nothing else to
+    split — so any even world size works."""
+    world = dist.get_world_size(group)
+    eps_half = eps_half.contiguous()
+    parts = [torch.empty_like(eps_half) for _ in range(world)]
+    dist.all_gather(parts, eps_half, group=group)
+    return torch.cat([parts[0], parts[1]], dim=0)

@@ -70,12 +70,38 @@ def predict_noise_xl(unet, scheduler, timestep, latents, text_embeddings, add_te
     return _cfg(noise_pred, guidance_scale)
 
 
-def _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_scale, total_timesteps, start_timesteps):
+def _cfg_split_world(group):
+    import torch.distributed as dist
+
+    if group is False or not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    w = dist.get_world_size(group)
+    return (w, dist.get_rank(group)) if w >= 2 and w % 2 == 0 else (1, 0)
+
+
+def _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_scale, total_timesteps, start_timesteps,
+                  cfg_split_group=False):
+    """cfg_split_group: False = single process; None / a process group = split the CFG pair of every (serial) step
+    over the ranks — even ranks run the unconditional sample, odd ranks the conditional one, one 64 KiB all-gather per
+    step (the partial denoise is the serial 77 % of a text-slider iteration)."""
+    world, rank = _cfg_split_world(cfg_split_group)
+    if world > 1:
+        from . import parallel
+
+        n = latents.shape[0]
+        lo = (rank % 2) * n
+        text_half = text_embeddings[lo:lo + n]
+        added_half = None if added is None else {k: v[lo:lo + n] for k, v in added.items()}
     host = getattr(scheduler, "timesteps_host", None)
     steps = host[start_timesteps:total_timesteps] if host is not None else scheduler.timesteps[start_timesteps:total_timesteps]
     for timestep in steps:  # python ints: nothing in the loop reads the device back
         x = scheduler.scale_model_input(latents, timestep)
-        noise_pred = _unet_pair(unet, x, timestep, text_embeddings, added)
+        if world > 1:
+            kwargs = {"added_cond_kwargs": added_half} if added_half is not None else {}
+            half = unet(x, timestep, encoder_hidden_states=text_half, **kwargs).sample
+            noise_pred = parallel.cfg_split_eps(half, cfg_split_group)
+        else:
+            noise_pred = _unet_pair(unet, x, timestep, text_embeddings, added)
         a_t, a_prev = scheduler._alphas_for(timestep)
         # fused: eps = u + g (c - u);  x_{t-1} = DDIM(eps, x_t)
         _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), a_t, a_prev,
@@ -85,17 +111,17 @@ def _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_sca
 
 @torch.no_grad()
 def diffusion(unet, scheduler, latents, text_embeddings, total_timesteps: int = 1000, start_timesteps=0,
-              guidance_scale=7.5, **kwargs):
+              guidance_scale=7.5, cfg_split_group=False, **kwargs):
     return _denoise_loop(unet, scheduler, latents, text_embeddings, None, guidance_scale, total_timesteps,
-                         start_timesteps)
+                         start_timesteps, cfg_split_group)
 
 
 @torch.no_grad()
 def diffusion_xl(unet, scheduler, latents, text_embeddings, add_text_embeddings, add_time_ids,
-                 guidance_scale: float = 1.0, total_timesteps: int = 1000, start_timesteps=0):
+                 guidance_scale: float = 1.0, total_timesteps: int = 1000, start_timesteps=0, cfg_split_group=False):
     added = {"text_embeds": add_text_embeddings, "time_ids": add_time_ids}
     return _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_scale, total_timesteps,
-                         start_timesteps)
+                         start_timesteps, cfg_split_group)
 
 
 def get_add_time_ids(height: int, width: int, dynamic_crops: bool = False, dtype: torch.dtype = torch.float32):

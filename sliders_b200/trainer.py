@@ -67,7 +67,8 @@ class PromptEmbedsPair:
 
 
 def _world(group=None):
-    if dist.is_available() and dist.is_initialized():
+    """(world size, rank) of `group` (None = default group); `group=False` forces the single-process path."""
+    if group is not False and dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
     return 1, 0
 
@@ -91,9 +92,11 @@ def text_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler,
     """train_lora_xl.py:162-347.  Returns the (detached) loss.
 
     Under torch.distributed (one process per GPU) the four conditioned predictions are sharded one per rank
-    (BASELINE config 3): the serial partial denoise runs replicated (same seed on every rank), the three frozen
+    (BASELINE config 3): the three frozen
     predictions are broadcast to the rank that owns the grad-carrying `target` prediction, that rank back-propagates,
-    and ONE all-reduce of the flat LoRA gradient buffer makes every replica take the same AdamW step."""
+    and ONE all-reduce of the flat LoRA gradient buffer makes every replica take the same AdamW step.  The serial
+    partial denoise is CFG-split: even ranks run the unconditional sample of each step, odd ranks the conditional one,
+    with one 64 KiB all-gather per step (train_util._denoise_loop)."""
     device = device or unet.device
     with torch.no_grad():
         noise_scheduler.set_timesteps(max_denoising_steps, device=device)
@@ -116,12 +119,16 @@ def text_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler,
         with network:                                                                   # :205-227
             denoised_latents = train_util.diffusion_xl(
                 unet, noise_scheduler, latents, **_xl_inputs(prompt_pair, prompt_pair.target, add_time_ids),
-                start_timesteps=0, total_timesteps=timesteps_to, guidance_scale=3)
+                start_timesteps=0, total_timesteps=timesteps_to, guidance_scale=3,
+                **({"cfg_split_group": group} if _world(group)[0] > 1 else {}))
         noise_scheduler.set_timesteps(1000)
         current_timestep = noise_scheduler.timesteps[int(timesteps_to * 1000 / max_denoising_steps)]
         # outside `with network:` the adaptors are inert (:236-297)
         world, rank = _world(group)
-        owner = {name: i % world for i, name in enumerate(("positive", "neutral", "unconditional", "target"))}
+        # the grad-carrying prediction (forward + backward, ~4x a frozen one) gets a rank of its own
+        owner = {"target": world - 1}
+        for i, name in enumerate(("positive", "neutral", "unconditional")):
+            owner[name] = i % max(world - 1, 1)
         preds = {}
         for name in ("positive", "neutral", "unconditional"):
             if owner[name] == rank:

@@ -314,7 +314,7 @@ def predict_noise_xl(unet, sched, t, lat, text_embeddings, add_text_embeddings, 
         out = out + net.multiplier * (torch.einsum("oc,bchw->bohw", net.a, lat.float()) + net.b[None, :, None, None])
     return out
 def diffusion_xl(unet, sched, lat, text_embeddings, add_text_embeddings, add_time_ids, guidance_scale=1.0,
-                 total_timesteps=1000, start_timesteps=0):
+                 total_timesteps=1000, start_timesteps=0, cfg_split_group=False):
     calls.append("denoise")
     return lat * 0.9 + 0.01 * total_timesteps
 train_util.predict_noise_xl, train_util.diffusion_xl = predict_noise_xl, diffusion_xl
@@ -360,5 +360,6 @@ def test_text_slider_step_sharded_two_ranks_gloo(tmp_path):
     assert r0["losses"] == r1["losses"]
     # iteration 0 has a fixed step count and rank 0's noise: same loss as the single process
     assert abs(r0["losses"][0] - s["losses"][0]) < 1e-6
-    assert r0["calls"].count("predict") == 6 and r1["calls"].count("predict") == 6  # 2 of the 4 predictions each
+    # rank 1 owns the grad-carrying target prediction (forward + backward), rank 0 the three frozen ones
+    assert r0["calls"].count("predict") == 9 and r1["calls"].count("predict") == 3
     assert s["calls"].count("predict") == 12
