@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kBwdThreads, AttnBwdCfg<ND>::kMinBlocks)
   constexpr int kStages = AttnBwdCfg<ND>::kStages;
   constexpr uint32_t kRBytes = AttnBwdCfg<ND>::kRBytes;
   constexpr uint32_t kTBytes = AttnBwdCfg<ND>::kTBytes;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kBwdThreads, AttnBwdCfg<ND>::kMinBlocks)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const int n = (p.n_stream + 63) >> 6;
   const int dsteps = (p.d + 15) >> 4;
   const size_t stat_base = (static_cast<size_t>(b) * gridDim.y + head) * p.Sq;
@@ -306,6 +308,8 @@ __global__ void __launch_bounds__(kBwdThreads, AttnBwdCfg<ND>::kMinBlocks)
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int ldo,
                                      const __nv_bfloat16* __restrict__ dout, int lddo, float* __restrict__ dsum,
                                      int B, int heads, int Sq, int d) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(B) * Sq * heads;
   if (idx >= total) return;
@@ -334,7 +338,7 @@ static int launch_attention_bwd(cudaStream_t stream, const AttnBwdParams& p, dim
                                           AttnBwdCfg<ND>::kSmem));
     attr_set = true;
   }
-  attention_bwd_kernel<ND><<<grid, kBwdThreads, AttnBwdCfg<ND>::kSmem, stream>>>(p);
+  SB200_CUDA_CHECK(launch_pdl(attention_bwd_kernel<ND>, grid, dim3(kBwdThreads), AttnBwdCfg<ND>::kSmem, stream, p));
   SB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -356,6 +360,7 @@ extern "C" int sb200_attention_bwd(void* handle, void* stream, const void* q, in
                                    const void* v, int ldv, const void* o, int ldo, const void* dout, int lddo,
                                    const float* lse, float* dsum, void* dq, int lddq, void* dk, int lddk, void* dv,
                                    int lddv, int B, int heads, int Sq, int Skv, int head_dim, float scale) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "attention_bwd: NULL handle");
   SB200_REQUIRE(B > 0 && heads > 0 && Sq > 0 && Skv > 0, "attention_bwd: bad dims");
@@ -369,9 +374,9 @@ extern "C" int sb200_attention_bwd(void* handle, void* stream, const void* q, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     const size_t total = static_cast<size_t>(B) * Sq * heads;
-    attn_bwd_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(o), ldo, static_cast<const __nv_bfloat16*>(dout), lddo, dsum, B, heads,
-        Sq, head_dim);
+    SB200_CUDA_CHECK(launch_pdl(attn_bwd_prep_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s,
+                                static_cast<const __nv_bfloat16*>(o), ldo, static_cast<const __nv_bfloat16*>(dout), lddo,
+                                dsum, B, heads, Sq, head_dim));
     SB200_CUDA_CHECK(cudaGetLastError());
   }
   int st;

@@ -75,6 +75,8 @@ __device__ __forceinline__ void gn_bwd_load(const GnBwdArgs& a, int b, int c, co
 }
 
 __global__ void gn_bwd_stats_kernel(GnBwdArgs a, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sh[];  // [rows_par][C][2]
   const int nvec = a.C >> 3;
   const int cv = threadIdx.x % nvec, r0 = threadIdx.x / nvec, rows_par = blockDim.x / nvec;
@@ -128,6 +130,8 @@ __global__ void gn_bwd_stats_kernel(GnBwdArgs a, float* __restrict__ partial) {
 
 __global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ final_m, int chunks,
                                        int groups, float inv_n) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, lane = threadIdx.x & 31;
   for (int g = threadIdx.x >> 5; g < groups; g += blockDim.x >> 5) {
     float S1 = 0.f, S2 = 0.f;
@@ -149,6 +153,8 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, float*
 }
 
 __global__ void gn_bwd_apply_kernel(GnBwdArgs a, const float* __restrict__ final_m) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = a.C >> 3;
   const int cv = threadIdx.x % nvec, r0 = threadIdx.x / nvec, rows_par = blockDim.x / nvec;
   const int b = blockIdx.y, c = cv << 3;
@@ -197,6 +203,8 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ld
                                      const __nv_bfloat16* __restrict__ dy, int lddy,
                                      const __nv_bfloat16* __restrict__ add, int ldadd,
                                      __nv_bfloat16* __restrict__ dx, int lddx, int M, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31, nvec = C >> 3;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ldx;
@@ -282,6 +290,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
 
 __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ pre, int ldp, __nv_bfloat16* __restrict__ out,
                              int ldo, int M, int F) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = F >> 3;
   const size_t total = static_cast<size_t>(M) * nvec;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -300,6 +310,8 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ pre, int ldp, __n
 __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, int ldp,
                                  const __nv_bfloat16* __restrict__ dout, int lddo,
                                  __nv_bfloat16* __restrict__ dpre, int lddp, int M, int F) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = F >> 3;
   const size_t total = static_cast<size_t>(M) * nvec;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -326,6 +338,8 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, int ldp,
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b,
                            int ldb, const __nv_bfloat16* __restrict__ c3, int ldc, __nv_bfloat16* __restrict__ out,
                            int ldo, int M, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C >> 3;
   const size_t total = static_cast<size_t>(M) * nvec;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -349,6 +363,8 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, int lda, const _
 // nearest x2 upsample backward: dx[b,y,x,:] = sum of the 2x2 block of dy
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int B,
                                       int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C >> 3;
   const size_t total = static_cast<size_t>(B) * H * W * nvec;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -379,6 +395,8 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv
 // stride-2 conv input gradient helper: z[b, 2i, 2j, :] = dy[b, i, j, :], zero elsewhere ([B,2Ho,2Wo,C])
 __global__ void zero_stuff_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ z, int B, int Ho,
                                   int Wo, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C >> 3;
   const size_t total = static_cast<size_t>(B) * 2 * Ho * 2 * Wo * nvec;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -400,6 +418,8 @@ __global__ void zero_stuff_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfl
 __global__ void conv_out_bwd_kernel(const void* __restrict__ deps, int deps_f32,
                                     const __nv_bfloat16* __restrict__ w /*[4][3][3][C]*/,
                                     __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C >> 3;
   const size_t total = static_cast<size_t>(B) * H * W * nvec;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -439,6 +459,8 @@ __global__ void conv_out_bwd_kernel(const void* __restrict__ deps, int deps_f32,
 // per-batch column sum: out[b, c] = sum_hw dy[b, hw, c]   (gradient of the time-embedding row bias)
 // grid (C/8 / vec_per_block, B); block = (vec_per_block, rows_par)
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, int ld, float* __restrict__ out, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sh[];  // [rows_par][vpb*8]
   const int vpb = blockDim.x, rows_par = blockDim.y;
   const int cv = blockIdx.x * vpb + threadIdx.x;
@@ -478,6 +500,8 @@ constexpr int kVB = 32;  // 8-channel vectors per block in the wgrad / rank-upda
 // T[m, j] = sum_c A[m, c] * Bt[j, c]     (Bt: [r][C] bf16, row stride ldb)  -> T fp32 [M, r]
 __global__ void lora_proj_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ Bt,
                                  int ldb, float* __restrict__ T, int M, int C, int r, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31, nvec = C >> 3;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     float acc[kMaxR];
@@ -514,6 +538,8 @@ __global__ void lora_proj_kernel(const __nv_bfloat16* __restrict__ A, int lda, c
 template <int R>
 __global__ void lora_wgrad_kernel(const __nv_bfloat16* __restrict__ A, int lda, const float* __restrict__ T,
                                   float* __restrict__ partial, int M, int C, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[4][kVB][8 * R];
   const int cv = blockIdx.y * kVB + threadIdx.x;
   const int nvec = C >> 3;
@@ -555,6 +581,8 @@ __global__ void lora_wgrad_kernel(const __nv_bfloat16* __restrict__ A, int lda, 
 // G[c * gs_c + j * gs_r] (+)= scale * sum_chunks partial[chunk][c][j]
 __global__ void lora_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ G, int chunks, int C,
                                          int r, int gs_c, int gs_r, float scale, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * r) return;
   float s = 0.f;
@@ -569,6 +597,8 @@ template <int R>
 __global__ void lora_rank_update_kernel(__nv_bfloat16* __restrict__ dX, int ldx, const float* __restrict__ U,
                                         const __nv_bfloat16* __restrict__ D, int ldd, float scale, int M, int C,
                                         int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C >> 3;
   const int cv = blockIdx.y * kVB + threadIdx.x;
   if (cv >= nvec) return;
@@ -613,6 +643,8 @@ __device__ __forceinline__ const __nv_bfloat16* conv_src(const ConvGeom& g, size
 // T[p, j] = sum_{tap, c} x[p*stride + tap - 1, c] * D[j][tap][c]    one warp per output pixel
 __global__ void lora_conv_proj_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ D /*[r][3][3][C]*/,
                                       float* __restrict__ T, int r) {
+  pdl_trigger();
+  pdl_wait();
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31, nvec = g.C >> 3;
   const int P = g.B * g.Ho * g.Wo;
   for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P; p += gridDim.x * wpb) {
@@ -652,6 +684,8 @@ __global__ void lora_conv_proj_kernel(ConvGeom g, const __nv_bfloat16* __restric
 template <int R>
 __global__ void lora_conv_wgrad_kernel(ConvGeom g, const float* __restrict__ U, float* __restrict__ partial,
                                        int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[4][kVB][8 * R];
   const int cv = blockIdx.y * kVB + threadIdx.x, nvec = g.C >> 3, tap = blockIdx.z;
   const int P = g.B * g.Ho * g.Wo;
@@ -700,6 +734,8 @@ template <int R>
 __global__ void lora_conv_rank_update_kernel(__nv_bfloat16* __restrict__ dX, int B, int H, int W, int C, int Ho,
                                              int Wo, int stride, const float* __restrict__ U,
                                              const __nv_bfloat16* __restrict__ D, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int nvec = C >> 3;
   const size_t total = static_cast<size_t>(B) * H * W * nvec;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -759,6 +795,8 @@ __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2
 
 __global__ void adamw_kernel(const AdamTensor* __restrict__ table, float decay, float one_m_beta1, float beta2,
                              float one_m_beta2, float eps, float neg_step_size, float bc2_sqrt) {
+  pdl_trigger();
+  pdl_wait();
   const AdamTensor t = table[blockIdx.y];
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < t.n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -795,6 +833,7 @@ extern "C" int sb200_groupnorm_bwd(void* handle, void* stream, const void* x0, i
                                    int ldx1, int C1, const void* gamma, const void* beta, const void* dy, int lddy,
                                    const void* add, int ldadd, void* dx, int lddx, int B, int HW, int groups,
                                    int silu, const float* fwd_stats, float* ws) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "groupnorm_bwd: NULL handle");
   if (!x1) C1 = 0;
@@ -830,18 +869,16 @@ extern "C" int sb200_groupnorm_bwd(void* handle, void* stream, const void* x0, i
   chunks = (HW + rows_per_block - 1) / rows_per_block;
   a.rows_per_block = rows_per_block;
   float* final_m = ws + static_cast<size_t>(B) * kGnBwdMaxChunks * groups * 2;
-  gn_bwd_stats_kernel<<<dim3(chunks, B), threads, sizeof(float) * 2 * C * rows_par, s>>>(a, ws);
-  SB200_CUDA_CHECK(cudaGetLastError());
-  gn_bwd_finalize_kernel<<<B, 1024, 0, s>>>(ws, final_m, chunks, groups, 1.f / (static_cast<float>(HW) * a.cpg));
-  SB200_CUDA_CHECK(cudaGetLastError());
-  gn_bwd_apply_kernel<<<dim3(chunks, B), threads, 0, s>>>(a, final_m);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(gn_bwd_stats_kernel, dim3(dim3(chunks, B)), dim3(threads), sizeof(float) * 2 * C * rows_par, s, a, ws));
+  SB200_CUDA_CHECK(launch_pdl(gn_bwd_finalize_kernel, dim3(B), dim3(1024), 0, s, ws, final_m, chunks, groups, 1.f / (static_cast<float>(HW) * a.cpg)));
+  SB200_CUDA_CHECK(launch_pdl(gn_bwd_apply_kernel, dim3(dim3(chunks, B)), dim3(threads), 0, s, a, final_m));
   return 0;
 }
 
 extern "C" int sb200_layernorm_bwd(void* handle, void* stream, const void* x, int ldx, const void* gamma,
                                    const void* dy, int lddy, const void* add, int ldadd, void* dx, int lddx, int M,
                                    int C, float eps) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "layernorm_bwd: NULL handle");
   SB200_REQUIRE(M > 0 && C > 0 && C % 8 == 0 && C <= 2048, "layernorm_bwd: C=%d unsupported", C);
@@ -869,90 +906,90 @@ extern "C" int sb200_layernorm_bwd(void* handle, void* stream, const void* x, in
 }
 
 extern "C" int sb200_geglu(void* handle, void* stream, const void* pre, int ldp, void* out, int ldo, int M, int F) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && M > 0 && F > 0 && F % 8 == 0 && ldp % 8 == 0 && ldo % 8 == 0, "geglu: arguments");
-  geglu_kernel<<<grid_for(static_cast<size_t>(M) * F / 8, 256, ctx->num_sms), 256, 0,
-                 static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(pre), ldp, static_cast<bf*>(out), ldo, M, F);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(geglu_kernel, dim3(grid_for(static_cast<size_t>(M) * F / 8, 256, ctx->num_sms)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), static_cast<const bf*>(pre), ldp, static_cast<bf*>(out), ldo, M, F));
   return 0;
 }
 
 extern "C" int sb200_geglu_bwd(void* handle, void* stream, const void* pre, int ldp, const void* dout, int lddo,
                                void* dpre, int lddp, int M, int F) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && M > 0 && F > 0 && F % 8 == 0 && ldp % 8 == 0 && lddo % 8 == 0 && lddp % 8 == 0,
                 "geglu_bwd: arguments");
-  geglu_bwd_kernel<<<grid_for(static_cast<size_t>(M) * F / 8, 256, ctx->num_sms), 256, 0,
-                     static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(pre), ldp,
+  SB200_CUDA_CHECK(launch_pdl(geglu_bwd_kernel, dim3(grid_for(static_cast<size_t>(M) * F / 8, 256, ctx->num_sms)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), static_cast<const bf*>(pre), ldp,
                                                           static_cast<const bf*>(dout), lddo, static_cast<bf*>(dpre),
-                                                          lddp, M, F);
-  SB200_CUDA_CHECK(cudaGetLastError());
+                                                          lddp, M, F));
   return 0;
 }
 
 extern "C" int sb200_add(void* handle, void* stream, const void* a, int lda, const void* b, int ldb, const void* c,
                          int ldc, void* out, int ldo, int M, int C) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && a && b && out && M > 0 && C > 0 && C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 &&
                     ldo % 8 == 0 && (!c || ldc % 8 == 0),
                 "add: arguments");
-  add_kernel<<<grid_for(static_cast<size_t>(M) * C / 8, 256, ctx->num_sms), 256, 0,
-               static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(a), lda, static_cast<const bf*>(b), ldb,
-                                                    static_cast<const bf*>(c), ldc, static_cast<bf*>(out), ldo, M, C);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(add_kernel, dim3(grid_for(static_cast<size_t>(M) * C / 8, 256, ctx->num_sms)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), static_cast<const bf*>(a), lda, static_cast<const bf*>(b), ldb,
+                                                    static_cast<const bf*>(c), ldc, static_cast<bf*>(out), ldo, M, C));
   return 0;
 }
 
 extern "C" int sb200_upsample2x_bwd(void* handle, void* stream, const void* dy, void* dx, int B, int H, int W, int C) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && dy && dx && B > 0 && H > 0 && W > 0 && C % 8 == 0, "upsample2x_bwd: arguments");
-  upsample2x_bwd_kernel<<<grid_for(static_cast<size_t>(B) * H * W * C / 8, 256, ctx->num_sms), 256, 0,
-                          static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(dy), static_cast<bf*>(dx), B, H, W, C);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(upsample2x_bwd_kernel, dim3(grid_for(static_cast<size_t>(B) * H * W * C / 8, 256, ctx->num_sms)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), static_cast<const bf*>(dy), static_cast<bf*>(dx), B, H, W, C));
   return 0;
 }
 
 extern "C" int sb200_zero_stuff(void* handle, void* stream, const void* dy, void* z, int B, int Ho, int Wo, int C) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && dy && z && B > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, "zero_stuff: arguments");
-  zero_stuff_kernel<<<grid_for(static_cast<size_t>(B) * 4 * Ho * Wo * C / 8, 256, ctx->num_sms), 256, 0,
-                      static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(dy), static_cast<bf*>(z), B, Ho, Wo, C);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(zero_stuff_kernel, dim3(grid_for(static_cast<size_t>(B) * 4 * Ho * Wo * C / 8, 256, ctx->num_sms)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), static_cast<const bf*>(dy), static_cast<bf*>(z), B, Ho, Wo, C));
   return 0;
 }
 
 extern "C" int sb200_conv_out_bwd(void* handle, void* stream, const void* deps, int deps_f32, const void* w, void* dx,
                                   int B, int H, int W, int C) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && deps && w && dx && B > 0 && H > 0 && W > 0 && C % 8 == 0, "conv_out_bwd: arguments");
-  conv_out_bwd_kernel<<<grid_for(static_cast<size_t>(B) * H * W * C / 8, 256, ctx->num_sms), 256, 0,
-                        static_cast<cudaStream_t>(stream)>>>(deps, deps_f32, static_cast<const bf*>(w),
-                                                             static_cast<bf*>(dx), B, H, W, C);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(conv_out_bwd_kernel, dim3(grid_for(static_cast<size_t>(B) * H * W * C / 8, 256, ctx->num_sms)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), deps, deps_f32, static_cast<const bf*>(w),
+                                                             static_cast<bf*>(dx), B, H, W, C));
   return 0;
 }
 
 extern "C" int sb200_colsum(void* handle, void* stream, const void* dy, int ld, float* out, int B, int HW, int C) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && dy && out && B > 0 && HW > 0 && C % 8 == 0 && ld % 8 == 0, "colsum: arguments");
   const int vpb = 8, rows_par = 64;  // 64 channels per block: many blocks, each streams 128-byte row pieces
   dim3 grid((C / 8 + vpb - 1) / vpb, B), block(vpb, rows_par);
-  colsum_kernel<<<grid, block, sizeof(float) * rows_par * vpb * 8, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf*>(dy), ld, out, HW, C);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(colsum_kernel, dim3(grid), dim3(block), sizeof(float) * rows_par * vpb * 8, static_cast<cudaStream_t>(stream), 
+      static_cast<const bf*>(dy), ld, out, HW, C));
   return 0;
 }
 
 extern "C" int sb200_lora_proj(void* handle, void* stream, const void* A, int lda, const void* Bt, int ldb, float* T,
                                int M, int C, int r, int accumulate) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && A && Bt && T && M > 0 && C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && (r == 4 || r == 8),
                 "lora_proj: arguments (r=%d)", r);
   int blocks = (M + 7) / 8;
   if (blocks > ctx->num_sms * 16) blocks = ctx->num_sms * 16;
-  lora_proj_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(A), lda,
-                                                                          static_cast<const bf*>(Bt), ldb, T, M, C, r, accumulate);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(lora_proj_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const bf*>(A), lda,
+                                                                          static_cast<const bf*>(Bt), ldb, T, M, C, r, accumulate));
   return 0;
 }
 
@@ -969,6 +1006,7 @@ static int wgrad_chunks(Ctx* ctx, int rows, int cblocks, int* rows_per_block) {
 /* ws must hold SB200_WGRAD_WS_FLOATS(C, r) floats */
 extern "C" int sb200_lora_wgrad(void* handle, void* stream, const void* A, int lda, const float* T, float* G,
                                 int gs_c, int gs_r, float scale, int accumulate, int M, int C, int r, float* ws) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && A && T && G && ws && M > 0 && C % 8 == 0 && lda % 8 == 0 && (r == 4 || r == 8),
                 "lora_wgrad: arguments (r=%d)", r);
@@ -978,17 +1016,16 @@ extern "C" int sb200_lora_wgrad(void* handle, void* stream, const void* A, int l
   const int chunks = wgrad_chunks(ctx, M, cblocks, &rpb);
   dim3 grid(chunks, cblocks), block(kVB, 4);
   if (r == 4)
-    lora_wgrad_kernel<4><<<grid, block, 0, s>>>(static_cast<const bf*>(A), lda, T, ws, M, C, rpb);
+    SB200_CUDA_CHECK(launch_pdl(lora_wgrad_kernel<4>, dim3(grid), dim3(block), 0, s, static_cast<const bf*>(A), lda, T, ws, M, C, rpb));
   else
-    lora_wgrad_kernel<8><<<grid, block, 0, s>>>(static_cast<const bf*>(A), lda, T, ws, M, C, rpb);
-  SB200_CUDA_CHECK(cudaGetLastError());
-  lora_wgrad_reduce_kernel<<<(C * r + 255) / 256, 256, 0, s>>>(ws, G, chunks, C, r, gs_c, gs_r, scale, accumulate);
-  SB200_CUDA_CHECK(cudaGetLastError());
+    SB200_CUDA_CHECK(launch_pdl(lora_wgrad_kernel<8>, dim3(grid), dim3(block), 0, s, static_cast<const bf*>(A), lda, T, ws, M, C, rpb));
+  SB200_CUDA_CHECK(launch_pdl(lora_wgrad_reduce_kernel, dim3((C * r + 255) / 256), dim3(256), 0, s, ws, G, chunks, C, r, gs_c, gs_r, scale, accumulate));
   return 0;
 }
 
 extern "C" int sb200_lora_rank_update(void* handle, void* stream, void* dX, int ldx, const float* U, const void* D,
                                       int ldd, float scale, int M, int C, int r) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && dX && U && D && M > 0 && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0 && (r == 4 || r == 8),
                 "lora_rank_update: arguments (r=%d)", r);
@@ -998,12 +1035,11 @@ extern "C" int sb200_lora_rank_update(void* handle, void* stream, void* dX, int 
   const int chunks = wgrad_chunks(ctx, M, cblocks, &rpb);
   dim3 grid(chunks, cblocks), block(kVB, 4);
   if (r == 4)
-    lora_rank_update_kernel<4><<<grid, block, 0, s>>>(static_cast<bf*>(dX), ldx, U, static_cast<const bf*>(D), ldd,
-                                                     scale, M, C, rpb);
+    SB200_CUDA_CHECK(launch_pdl(lora_rank_update_kernel<4>, dim3(grid), dim3(block), 0, s, static_cast<bf*>(dX), ldx, U, static_cast<const bf*>(D), ldd,
+                                                     scale, M, C, rpb));
   else
-    lora_rank_update_kernel<8><<<grid, block, 0, s>>>(static_cast<bf*>(dX), ldx, U, static_cast<const bf*>(D), ldd,
-                                                     scale, M, C, rpb);
-  SB200_CUDA_CHECK(cudaGetLastError());
+    SB200_CUDA_CHECK(launch_pdl(lora_rank_update_kernel<8>, dim3(grid), dim3(block), 0, s, static_cast<bf*>(dX), ldx, U, static_cast<const bf*>(D), ldd,
+                                                     scale, M, C, rpb));
   return 0;
 }
 
@@ -1018,6 +1054,7 @@ static int fill_geom(ConvGeom* g, const void* x0, int ldx0, int C0, const void* 
 
 extern "C" int sb200_lora_conv_proj(void* handle, void* stream, const void* x0, int ldx0, int C0, const void* x1,
                                     int ldx1, int C1, const void* D, float* T, int B, int H, int W, int stride, int r) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && x0 && D && T && C0 % 8 == 0 && (!x1 || C1 % 8 == 0) && (stride == 1 || stride == 2) &&
                     (r == 4 || r == 8),
@@ -1027,8 +1064,7 @@ extern "C" int sb200_lora_conv_proj(void* handle, void* stream, const void* x0, 
   const int P = B * g.Ho * g.Wo;
   int blocks = (P + 7) / 8;
   if (blocks > ctx->num_sms * 16) blocks = ctx->num_sms * 16;
-  lora_conv_proj_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, static_cast<const bf*>(D), T, r);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(lora_conv_proj_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), g, static_cast<const bf*>(D), T, r));
   return 0;
 }
 
@@ -1036,6 +1072,7 @@ extern "C" int sb200_lora_conv_proj(void* handle, void* stream, const void* x0, 
 extern "C" int sb200_lora_conv_wgrad(void* handle, void* stream, const void* x0, int ldx0, int C0, const void* x1,
                                      int ldx1, int C1, const float* U, float* G, float scale, int accumulate, int B,
                                      int H, int W, int stride, int r, float* ws) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && x0 && U && G && ws && C0 % 8 == 0 && (!x1 || C1 % 8 == 0) && (stride == 1 || stride == 2) &&
                     (r == 4 || r == 8),
@@ -1049,37 +1086,36 @@ extern "C" int sb200_lora_conv_wgrad(void* handle, void* stream, const void* x0,
   const int chunks = wgrad_chunks(ctx, P, cblocks * 9, &rpb);
   dim3 grid(chunks, cblocks, 9), block(kVB, 4);
   if (r == 4)
-    lora_conv_wgrad_kernel<4><<<grid, block, 0, s>>>(g, U, ws, rpb);
+    SB200_CUDA_CHECK(launch_pdl(lora_conv_wgrad_kernel<4>, dim3(grid), dim3(block), 0, s, g, U, ws, rpb));
   else
-    lora_conv_wgrad_kernel<8><<<grid, block, 0, s>>>(g, U, ws, rpb);
-  SB200_CUDA_CHECK(cudaGetLastError());
+    SB200_CUDA_CHECK(launch_pdl(lora_conv_wgrad_kernel<8>, dim3(grid), dim3(block), 0, s, g, U, ws, rpb));
   const int C9 = 9 * g.C;
   // G[j][tap*C + c]: gs_c = 1, gs_r = 9*C
-  lora_wgrad_reduce_kernel<<<(C9 * r + 255) / 256, 256, 0, s>>>(ws, G, chunks, C9, r, 1, C9, scale, accumulate);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(lora_wgrad_reduce_kernel, dim3((C9 * r + 255) / 256), dim3(256), 0, s, ws, G, chunks, C9, r, 1, C9, scale, accumulate));
   return 0;
 }
 
 extern "C" int sb200_lora_conv_rank_update(void* handle, void* stream, void* dX, const float* U, const void* D,
                                            float scale, int B, int H, int W, int C, int stride, int r) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && dX && U && D && C % 8 == 0 && (stride == 1 || stride == 2) && (r == 4 || r == 8),
                 "lora_conv_rank_update: arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int blocks = grid_for(static_cast<size_t>(B) * H * W * C / 8, 256, ctx->num_sms);
   if (r == 4)
-    lora_conv_rank_update_kernel<4><<<blocks, 256, 0, s>>>(static_cast<bf*>(dX), B, H, W, C, H / stride, W / stride,
-                                                          stride, U, static_cast<const bf*>(D), scale);
+    SB200_CUDA_CHECK(launch_pdl(lora_conv_rank_update_kernel<4>, dim3(blocks), dim3(256), 0, s, static_cast<bf*>(dX), B, H, W, C, H / stride, W / stride,
+                                                          stride, U, static_cast<const bf*>(D), scale));
   else
-    lora_conv_rank_update_kernel<8><<<blocks, 256, 0, s>>>(static_cast<bf*>(dX), B, H, W, C, H / stride, W / stride,
-                                                          stride, U, static_cast<const bf*>(D), scale);
-  SB200_CUDA_CHECK(cudaGetLastError());
+    SB200_CUDA_CHECK(launch_pdl(lora_conv_rank_update_kernel<8>, dim3(blocks), dim3(256), 0, s, static_cast<bf*>(dX), B, H, W, C, H / stride, W / stride,
+                                                          stride, U, static_cast<const bf*>(D), scale));
   return 0;
 }
 
 /* table: device array of n_tensors {p, g, m, v (device pointers), n (int64)} records (5 x 8 bytes each) */
 extern "C" int sb200_adamw(void* handle, void* stream, const void* table, int n_tensors, long long max_numel,
                            double lr, double beta1, double beta2, double eps, double weight_decay, int step) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && table && n_tensors > 0 && max_numel > 0 && step >= 1, "adamw: arguments");
   static_assert(sizeof(AdamTensor) == 40, "AdamTensor layout");
@@ -1087,10 +1123,9 @@ extern "C" int sb200_adamw(void* handle, void* stream, const void* table, int n_
   const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   int bx = static_cast<int>((max_numel + 255) / 256);
   if (bx > 64) bx = 64;
-  adamw_kernel<<<dim3(bx, n_tensors), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  SB200_CUDA_CHECK(launch_pdl(adamw_kernel, dim3(dim3(bx, n_tensors)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const AdamTensor*>(table), static_cast<float>(1.0 - lr * weight_decay),
       static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
-      static_cast<float>(eps), static_cast<float>(-(lr / bc1)), static_cast<float>(sqrt(bc2)));
-  SB200_CUDA_CHECK(cudaGetLastError());
+      static_cast<float>(eps), static_cast<float>(-(lr / bc1)), static_cast<float>(sqrt(bc2))));
   return 0;
 }

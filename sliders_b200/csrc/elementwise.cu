@@ -68,6 +68,8 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, bool silu_
 }
 
 __global__ void __launch_bounds__(kSlWarps * 32) small_linear_kernel(SmallLinearArgs a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float t_sh[kSlMaxM][kSlMaxR * 4];  // LoRA down-projection of every row: [M][groups*r]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = a.K >> 3;
@@ -291,6 +293,7 @@ using namespace sb200;
 
 extern "C" int sb200_sinusoid(void* handle, void* stream, const float* values, int n, int dim, void* out,
                               int ldo) {
+  pdl_hint() = true;
   SB200_REQUIRE(handle && values && out, "sinusoid: NULL argument");
   SB200_REQUIRE(n > 0 && dim > 0 && dim % 2 == 0 && ldo >= dim, "sinusoid: dims");
   const int total = n * (dim / 2);
@@ -303,6 +306,7 @@ extern "C" int sb200_sinusoid(void* handle, void* stream, const float* values, i
 extern "C" int sb200_small_linear(void* handle, void* stream, const void* x, int ldx, const void* w, int ldw,
                                   const void* bias, void* out, int ldo, int M, int N, int K, int act_in,
                                   int act_out, const sb200_lora* lora, const void* resid) {
+  pdl_hint() = true;
   SB200_REQUIRE(handle && x && w && out, "small_linear: NULL argument");
   SB200_REQUIRE(M > 0 && M <= kSlMaxM, "small_linear: M=%d must be in [1, %d]", M, kSlMaxM);
   SB200_REQUIRE(N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "small_linear: dims");
@@ -332,14 +336,14 @@ extern "C" int sb200_small_linear(void* handle, void* stream, const void* x, int
     a.scale_dev = lora->scale_dev;
   }
   const int cols_per_block = kSlWarps * kSlColsPerWarp;
-  small_linear_kernel<<<(N + cols_per_block - 1) / cols_per_block, kSlWarps * 32, 0,
-                        static_cast<cudaStream_t>(stream)>>>(a);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(small_linear_kernel, dim3((N + cols_per_block - 1) / cols_per_block),
+                              dim3(kSlWarps * 32), 0, static_cast<cudaStream_t>(stream), a));
   return 0;
 }
 
 extern "C" int sb200_conv_in(void* handle, void* stream, const void* latent_nchw, int latent_is_f32,
                              const void* w, const void* bias, void* out, int B, int H, int W, int Cout) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && latent_nchw && w && out, "conv_in: NULL argument");
   SB200_REQUIRE(Cout % 8 == 0 && Cout * 36 * 2 <= 48 * 1024, "conv_in: Cout=%d unsupported", Cout);
@@ -363,6 +367,7 @@ extern "C" int sb200_conv_in(void* handle, void* stream, const void* latent_nchw
 
 extern "C" int sb200_conv_out(void* handle, void* stream, const void* x, const void* w, const void* bias,
                               void* out, int out_is_f32, int B, int H, int W, int Cin) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && x && w && out, "conv_out: NULL argument");
   SB200_REQUIRE(Cin % 8 == 0 && Cin * 36 * 2 <= 48 * 1024, "conv_out: Cin=%d unsupported", Cin);
@@ -386,6 +391,7 @@ extern "C" int sb200_conv_out(void* handle, void* stream, const void* x, const v
 
 extern "C" int sb200_upsample2x(void* handle, void* stream, const void* x, void* out, int B, int H, int W,
                                 int C) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && x && out, "upsample2x: NULL argument");
   SB200_REQUIRE(C % 8 == 0, "upsample2x: C=%d must be a multiple of 8", C);
@@ -401,6 +407,7 @@ extern "C" int sb200_upsample2x(void* handle, void* stream, const void* x, void*
 extern "C" int sb200_cfg_ddim(void* handle, void* stream, const void* eps2, int eps_is_f32, float g,
                               const void* x, float a_t, float a_prev, void* x_prev, void* eps_out,
                               int out_is_f32, int64_t n) {
+  pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && eps2 && n > 0, "cfg_ddim: bad arguments");
   SB200_REQUIRE(x || eps_out, "cfg_ddim: nothing to write");

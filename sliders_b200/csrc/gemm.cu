@@ -107,6 +107,7 @@ __device__ __forceinline__ void lora_apply(float* f, const float* t, const float
 // `lane == 0` branch (ptxas then wraps each uniform-datapath instruction in an ELECT / BRA.U.ANY retry loop).
 template <int kCtas, bool kElect>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   const int unit = blockIdx.x / kCtas;          // persistent work unit (CTA or CTA pair)
@@ -589,12 +591,13 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
     ctx->gemm_attr_set = true;
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
+  pdl_hint() = total <= 2 * ctx->num_sms;
   if (ctas == 1) {
     const int grid = total < ctx->num_sms ? total : ctx->num_sms;
     if (elect)
-      gemm_kernel<1, true><<<grid, kGemmThreads, smem, stream>>>(p);
+      SB200_CUDA_CHECK(launch_pdl(gemm_kernel<1, true>, dim3(grid), dim3(kGemmThreads), smem, stream, p));
     else
-      gemm_kernel<1, false><<<grid, kGemmThreads, smem, stream>>>(p);
+      SB200_CUDA_CHECK(launch_pdl(gemm_kernel<1, false>, dim3(grid), dim3(kGemmThreads), smem, stream, p));
   } else {
     const int units = ctx->num_sms / 2;
     const int grid = 2 * (total < units ? total : units);

@@ -27,6 +27,8 @@ constexpr int kGnMaxChunks = 128;
 // Deterministic (atomic-free) reduction: per-thread partials -> shared memory -> one thread per group sums
 // its channels in a fixed order -> partial[b][chunk][g] in global; gn_finalize_kernel sums the chunks in order.
 __global__ void gn_stats_kernel(GnArgs a, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sh[];  // [rows_par][C][2]
   const int nvec = a.C >> 3;
   const int cv = threadIdx.x % nvec;
@@ -83,6 +85,8 @@ __global__ void gn_stats_kernel(GnArgs a, float* __restrict__ partial) {
 // final[b][g] = {mean, rstd}; one warp per group, fixed-order lane-strided sum + shuffle tree (deterministic)
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ final_stats,
                                    int chunks, int groups, float inv_n, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31;
   for (int g = threadIdx.x >> 5; g < groups; g += blockDim.x >> 5) {
@@ -120,6 +124,8 @@ struct GnApplyArgs {
 // grid (chunks, B), block = (C/8) * rows_par threads like gn_stats_kernel: a thread owns one 8-channel vector,
 // folds (mean, rstd, gamma, beta) into scale/shift once and then streams its rows: 16 B in, 8 FMA (+SiLU), 16 B out.
 __global__ void gn_apply_kernel(GnApplyArgs a, const float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   const GnArgs& in = a.in;
   const int nvec = in.C >> 3;
   const int cv = threadIdx.x % nvec;
@@ -186,6 +192,8 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                  const __nv_bfloat16* __restrict__ gamma,
                                  const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                  int ldo, int M, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
@@ -264,6 +272,7 @@ extern "C" int sb200_groupnorm(void* handle, void* stream, const void* x0, int l
   SB200_REQUIRE(C / 8 <= 1024, "groupnorm: C=%d too large", C);
   SB200_REQUIRE(stats_ws && gamma && beta, "groupnorm: NULL argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  pdl_hint() = static_cast<long long>(B) * HW * C <= (16LL << 20);
   GnArgs a;
   a.x0 = static_cast<const __nv_bfloat16*>(x0);
   a.x1 = static_cast<const __nv_bfloat16*>(x1);
@@ -288,11 +297,10 @@ extern "C" int sb200_groupnorm(void* handle, void* stream, const void* x0, int l
   a.rows_per_block = rows_per_block;
   // workspace: partial[B][chunks][G][2] followed by final[B][G][2]
   float* final_stats = stats_ws + static_cast<size_t>(B) * kGnMaxChunks * groups * 2;
-  gn_stats_kernel<<<dim3(chunks, B), threads, sizeof(float) * 2 * C * rows_par, s>>>(a, stats_ws);
-  SB200_CUDA_CHECK(cudaGetLastError());
-  gn_finalize_kernel<<<B, 1024, 0, s>>>(stats_ws, final_stats, chunks, groups,
-                                      1.f / (static_cast<float>(HW) * a.cpg), eps);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(gn_stats_kernel, dim3(chunks, B), dim3(threads), sizeof(float) * 2 * C * rows_par, s, a,
+                              stats_ws));
+  SB200_CUDA_CHECK(launch_pdl(gn_finalize_kernel, dim3(B), dim3(1024), 0, s, stats_ws, final_stats, chunks, groups,
+                              1.f / (static_cast<float>(HW) * a.cpg), eps));
   GnApplyArgs ap;
   ap.in = a;
   ap.gamma = static_cast<const __nv_bfloat16*>(gamma);
@@ -302,8 +310,7 @@ extern "C" int sb200_groupnorm(void* handle, void* stream, const void* x0, int l
   ap.B = B;
   ap.eps = eps;
   ap.silu = silu;
-  gn_apply_kernel<<<dim3(chunks, B), threads, 0, s>>>(ap, final_stats);
-  SB200_CUDA_CHECK(cudaGetLastError());
+  SB200_CUDA_CHECK(launch_pdl(gn_apply_kernel, dim3(chunks, B), dim3(threads), 0, s, ap, final_stats));
   return 0;
 }
 
@@ -318,11 +325,12 @@ extern "C" int sb200_layernorm(void* handle, void* stream, const void* x, int ld
   const int max_blocks = ctx->num_sms * 16;
   if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pdl_hint() = static_cast<long long>(M) * C <= (8LL << 20);
 #define SB200_LN(NV)                                                                                      \
-  layernorm_kernel<NV><<<blocks, warps * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx,            \
-                                                      static_cast<const __nv_bfloat16*>(gamma),             \
-                                                      static_cast<const __nv_bfloat16*>(beta),              \
-                                                      static_cast<__nv_bfloat16*>(out), ldo, M, C, eps)
+  SB200_CUDA_CHECK(launch_pdl(layernorm_kernel<NV>, dim3(blocks), dim3(warps * 32), 0, st,                 \
+                              static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(gamma), \
+                              static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(out), ldo, M, C, \
+                              eps))
   if (C <= 256)
     SB200_LN(1);
   else if (C <= 768)

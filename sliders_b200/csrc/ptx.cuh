@@ -21,6 +21,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its stream predecessor is still running; pdl_wait() blocks until the predecessor grid has completed and
+// its writes are visible (a no-op for ordinary launches), pdl_trigger() lets the successor's CTAs be scheduled early.
+// Every kernel calls pdl_trigger() first and pdl_wait() before its first global-memory access, so only the prologue
+// (barrier init, TMEM allocation, descriptor prefetch) and the launch latency overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -124,6 +124,8 @@ def main():
     with open(sys.argv[2]) as f:
         lines = [l for l in f if not l.startswith("==")]
     for row in csv.DictReader(lines):
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue
         name = row["Kernel Name"].split("(")[0].replace("sb200::", "").replace("void ", "").split("<")[0]
         v = float(row["Metric Value"].replace(",", ""))
         v = v / 1e3 if row["Metric Unit"] == "ns" else (v * 1e3 if row["Metric Unit"] == "ms" else v)
