@@ -215,8 +215,17 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
           tmem_ld_x32(tl + colS + c * 32, v);
           tmem_ld_wait();
           if (kv_left >= (c + 1) * 32) {
+            // four independent chains: a single running max is a 32-deep dependent chain (4 clk each)
+            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]),
+                  m3 = __uint_as_float(v[3]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 4; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+            }
+            mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -276,12 +285,20 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
         uint32_t pk[16];
         if (kv_left >= (c + 1) * 32) {  // warp-uniform: no masking code on full chunks
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // independent partial sums (no 32-deep add chain)
+          for (int i = 0; i < 16; i += 2) {
             const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_run));
             const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_run));
-            lsum += p0 + p1;
+            const float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 2]), p.scale_log2, -m_run));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 3]), p.scale_log2, -m_run));
+            s0 += p0;
+            s1 += p1;
+            s2 += p2;
+            s3 += p3;
             pk[i] = pack_bf16x2(p0, p1);
+            pk[i + 1] = pack_bf16x2(p2, p3);
           }
+          lsum += (s0 + s1) + (s2 + s3);
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
