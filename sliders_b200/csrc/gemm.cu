@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     if ((kElect || lane == 0) && leader) {
       const uint32_t idesc = umma_idesc_bf16(kBM * kCtas, p.bn);
       const uint32_t idesc_l = umma_idesc_bf16(kBM * kCtas, has_lora ? p.lora_rt : 16);
+      const uint32_t idesc_wl = umma_idesc_bf16(kBM * kCtas, p.bn + (has_lora ? p.lora_rt : 0));
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -312,10 +313,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
                   umma_ss_2cta(d_tmem + static_cast<uint32_t>(p.bn), adesc,
                                (static_cast<uint64_t>(kDescHi) << 32) | (l_lo + 2u * k), idesc_l, acc);
               } else {
-                umma_ss((p.debug & 16) ? (d_tmem ^ ((k & 1) ? 256u : 0u)) : d_tmem, adesc, bdesc, idesc, acc);  // debug 16: alternate accumulators
-                if (has_lora)
-                  umma_ss(d_tmem + static_cast<uint32_t>(p.bn), adesc,
-                          (static_cast<uint64_t>(kDescHi) << 32) | (l_lo + 2u * k), idesc_l, acc);
+                // The LoRA-down rows sit right behind the W rows in the stage and their accumulator columns right
+                // behind the tile's, so ONE UMMA of N = bn + rt covers both (each UMMA carries ~50 cycles of fixed
+                // cost on top of N/2: a separate N = 16 instruction per k-step cost +37 % main-loop time).
+                umma_ss((p.debug & 16) ? (d_tmem ^ ((k & 1) ? 256u : 0u)) : d_tmem, adesc, bdesc,
+                        has_lora ? idesc_wl : idesc, acc);  // debug 16: alternate accumulators
               }
             }
             // free the smem stage (in every CTA of the pair) once these MMAs retire
