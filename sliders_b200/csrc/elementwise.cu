@@ -28,7 +28,7 @@ __global__ void sinusoid_kernel(const float* __restrict__ values, int n, int dim
 // block = 8 warps, each warp owns kColsPerWarp output columns; x rows are read through L1.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSlWarps = 8;
-constexpr int kSlColsPerWarp = 4;
+constexpr int kSlColsPerWarp = 1;  // more, smaller blocks: M <= 64 rows, the kernel is latency-bound (53 -> ~15 us at N = 1280)
 constexpr int kSlMaxM = 64;
 constexpr int kSlMaxR = 8;
 

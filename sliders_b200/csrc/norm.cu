@@ -193,10 +193,18 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                  const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                  int ldo, int M, int C, float eps) {
   pdl_trigger();
-  pdl_wait();
+  // gamma / beta staged once per block (frozen parameters: readable before the predecessor grid has finished), so the
+  // 8 rows of a block do not each re-read 2 x C x 2 bytes through L1 / L2 — that doubled the kernel's memory traffic
+  extern __shared__ uint4 gb_sh[];  // [2][C / 8]
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    gb_sh[v] = __ldg(reinterpret_cast<const uint4*>(gamma) + v);
+    gb_sh[nvec + v] = __ldg(reinterpret_cast<const uint4*>(beta) + v);
+  }
+  __syncthreads();
+  pdl_wait();
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
        row += gridDim.x * warps_per_block) {
     const __nv_bfloat16* xr = x + static_cast<size_t>(row) * ldx;
@@ -238,8 +246,8 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
     for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < nvec) {
-        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + v * 8));
-        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + v * 8));
+        const uint4 gv = gb_sh[v];
+        const uint4 bv = gb_sh[nvec + v];
         const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
         const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
         uint32_t o[4];
@@ -327,7 +335,7 @@ extern "C" int sb200_layernorm(void* handle, void* stream, const void* x, int ld
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   pdl_hint() = static_cast<long long>(M) * C <= (8LL << 20);
 #define SB200_LN(NV)                                                                                      \
-  SB200_CUDA_CHECK(launch_pdl(layernorm_kernel<NV>, dim3(blocks), dim3(warps * 32), 0, st,                 \
+  SB200_CUDA_CHECK(launch_pdl(layernorm_kernel<NV>, dim3(blocks), dim3(warps * 32), static_cast<size_t>(C) * 4, st,                 \
                               static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(gamma), \
                               static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(out), ldo, M, C, \
                               eps))

@@ -318,6 +318,7 @@ class UNet2DConditionModel(nn.Module):
         self._packed.clear()
         self._lora_packs.clear()
         self._graphs.clear()
+        self.__dict__.pop("_train_graphs", None)
         self._slider_scale_dev = None
         return out
 
@@ -325,6 +326,7 @@ class UNet2DConditionModel(nn.Module):
         out = super().load_state_dict(*a, **k)
         self._packed.clear()
         self._graphs.clear()
+        self.__dict__.pop("_train_graphs", None)
         return out
 
     # ---- frozen-weight packing -----------------------------------------------------------------------

@@ -95,3 +95,31 @@ def test_image_slider_step_xl(dev):
         first = tot if first is None else first
         last = tot
     assert last < first, (first, last)
+
+
+def test_training_cuda_graphs_match_eager(dev):
+    """`unet.use_cuda_graph = True` replays the training forward and backward as two CUDA graphs
+    (sliders_b200/autograd.py::_TrainCapture): same kernels, same order -> bit-identical LoRA weights after two
+    optimisation steps, including the second step that reuses the captured graphs with updated weights."""
+    from sliders_b200 import trainer, train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+
+    fx = torch.load(os.path.join(GOLDEN, "tiny_xl.pt"))
+    results = {}
+    for mode in ("eager", "graph"):
+        pm, net = build_product(fx, dev)
+        net.requires_grad_(True)
+        pm.use_cuda_graph = mode == "graph"
+        opt = train_util.get_optimizer("AdamW")(net.prepare_optimizer_params(), lr=1e-3)
+        sched = create_noise_scheduler("ddim")
+        pair = _xl_pair(trainer, fx, dev)
+        losses = []
+        for it in range(3):
+            losses.append(float(trainer.text_slider_step_xl(pm, net, sched, opt, None, pair, timesteps_to=2, device=dev,
+                                                            weight_dtype=BF,
+                                                            generator=torch.Generator().manual_seed(40 + it))))
+        results[mode] = (losses, torch.cat([p.detach().float().reshape(-1) for p in net.parameters()]))
+        if mode == "graph":
+            assert len(pm.__dict__.get("_train_graphs", {})) == 1
+    assert results["eager"][0] == results["graph"][0], (results["eager"][0], results["graph"][0])
+    assert torch.equal(results["eager"][1], results["graph"][1])

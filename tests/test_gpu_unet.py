@@ -456,3 +456,75 @@ def test_full_sdxl_lora_gradients_vs_fp32_oracle(dev):
     total = (num / den) ** 0.5
     print(f"SDXL LoRA gradient rel-RMS vs fp32 oracle: global {total:.4f}, worst tensor {worst[0]:.4f} ({worst[1]})")
     assert total < 6e-2, (total, worst)
+
+
+def _oracle_lora_grads(om, net, slider, call):
+    """LoRA gradients of the fp32 oracle with W_eff = W + s * up @ down built from leaf tensors (the reference's
+    forward hook as a weight fold).  `call(functional_params) -> loss`."""
+    names = {"lora_unet_" + n.replace(".", "_"): n for n, _ in om.named_modules()}
+    params = dict(om.named_parameters())
+    leaves, eff = {}, {}
+    for l in net.unet_loras:
+        down = l.lora_down.weight.detach().float().requires_grad_()
+        up = l.lora_up.weight.detach().float().requires_grad_()
+        leaves[l.lora_name] = (down, up)
+        w = params[names[l.lora_name] + ".weight"]
+        if down.dim() == 4:
+            delta = torch.einsum("or,rikl->oikl", up[:, :, 0, 0], down)
+        else:
+            delta = up @ down
+        eff[names[l.lora_name] + ".weight"] = w + slider * l.scale * delta
+    call({**params, **eff}).backward()
+    return leaves
+
+
+@pytest.mark.parametrize("method,n_expected", [("full", None), ("xattn", None), ("selfattn", None)])
+def test_tiny_xl_gradients_other_train_methods(dev, method, n_expected):
+    """train methods that adapt the cross-attention projections (lora.py:176-188): the text-side K / V adaptors get
+    their gradients from the dK / dV pass of the attention backward; `selfattn` leaves every conv untouched."""
+    from oracle import unet as ounet
+    from sliders_b200 import lora as plora, synthetic
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    ocfg = ounet.UNetConfig.tiny_xl()
+    pm = UNet2DConditionModel(UNetConfig.from_dict(ocfg.__dict__))
+    synthetic.init_synthetic_(pm, seed=21)
+    om = ounet.UNet2DConditionModel(ocfg)
+    om.load_state_dict({k: v.float() for k, v in pm.state_dict().items()})
+    om = om.to(dev).eval().requires_grad_(False)
+    pm = pm.to(dev, BF).eval().requires_grad_(False)
+    om.load_state_dict({k: v.float() for k, v in pm.state_dict().items()})  # the bf16-rounded weights
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=2.0, train_method=method).to(dev, BF)
+    synthetic.init_lora_nonzero_(net, seed=22, up_std=0.05, reseed_down=True)
+    net.requires_grad_(True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 32, 32, generator=g).to(dev, BF)
+    ehs = torch.randn(2, 77, ocfg.cross_attention_dim, generator=g).to(dev, BF)
+    added = {"text_embeds": torch.randn(2, 128, generator=g).to(dev, BF),
+             "time_ids": torch.tensor([[256., 256., 0., 0., 256., 256.]] * 2, device=dev)}
+    goal = torch.randn(2, 4, 32, 32, generator=g).to(dev)
+    net.set_lora_slider(0.5)
+    with net:
+        pred = pm(x, 321, encoder_hidden_states=ehs, added_cond_kwargs=added).sample
+    assert pred.requires_grad
+    torch.nn.functional.mse_loss(pred.float(), goal).backward()
+    torch.cuda.synchronize()
+
+    def call(fp):
+        out = torch.func.functional_call(om, fp, (x.float(), 321, ehs.float()),
+                                         {"added_cond_kwargs": {k: v.float() for k, v in added.items()}}).sample
+        assert rel_rms(pred, out) < 3e-2
+        return torch.nn.functional.mse_loss(out, goal)
+
+    leaves = _oracle_lora_grads(om, net, 0.5, call)
+    num = den = 0.0
+    for l in net.unet_loras:
+        for got, ref in ((l.lora_down.weight.grad, leaves[l.lora_name][0].grad),
+                         (l.lora_up.weight.grad, leaves[l.lora_name][1].grad)):
+            assert got is not None and torch.isfinite(got).all(), l.lora_name
+            num += (got.float() - ref).pow(2).sum().item()
+            den += ref.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 5e-2, (method, (num / den) ** 0.5)
+    if method != "selfattn":
+        assert any("attn2_to_k" in l.lora_name for l in net.unet_loras)
