@@ -528,3 +528,46 @@ def test_tiny_xl_gradients_other_train_methods(dev, method, n_expected):
     assert (num / den) ** 0.5 < 5e-2, (method, (num / den) ** 0.5)
     if method != "selfattn":
         assert any("attn2_to_k" in l.lora_name for l in net.unet_loras)
+
+
+def test_full_size_inference_sweep_properties(dev):
+    """BASELINE config 5 at full size: SDXL, 1024 px, 16 samples (32 conditioned passes per step), DDIM, the slider
+    sweep of eval-scripts/generate_images_xl.py:495-508 under CUDA-graph replay — checked through size-independent
+    properties (the fp32 oracle needs minutes per step at this size): (1) slider 0 == adaptors never applied, bit for
+    bit; (2) with start_noise below every timestep the adaptors are gated off for any scale (generate_images_xl.py:
+    327-330), bit for bit; (3) replays are deterministic; (4) +s and -s move the result in opposite directions."""
+    from sliders_b200 import generate, lora as plora, synthetic
+    from sliders_b200.scheduler import create_noise_scheduler
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    with torch.device(dev):
+        pm = UNet2DConditionModel(UNetConfig.sdxl()).to(BF)
+    synthetic.init_synthetic_(pm, seed=1)
+    pm.requires_grad_(False)
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+    synthetic.init_lora_nonzero_(net, seed=2, up_std=0.02)
+    pm.use_cuda_graph = True
+    n, steps = 16, 3
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(n, 4, 128, 128, generator=g).to(dev, BF)
+    ehs = torch.randn(2 * n, 77, 2048, generator=g).to(dev, BF)
+    pooled = torch.randn(2 * n, 1280, generator=g).to(dev, BF)
+    tids = torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]] * (2 * n), device=dev)
+    sched = create_noise_scheduler("ddim")
+    run = lambda scale, start_noise: generate.denoise_loop(pm, net, sched, lat.clone(), ehs, pooled, tids,
+                                                           num_inference_steps=steps, guidance_scale=5.0, scale=scale,
+                                                           start_noise=start_noise)
+    base = run(0.0, 1000)
+    assert torch.isfinite(base).all() and base.shape == lat.shape
+    assert torch.equal(run(3.0, -1), base)          # gated off at every step
+    pos, pos2, neg = run(3.0, 1000), run(3.0, 1000), run(-3.0, 1000)
+    assert torch.equal(pos, pos2)
+    assert not torch.equal(pos, base)
+    d_pos, d_neg = (pos - base).float().flatten(), (neg - base).float().flatten()
+    assert torch.nn.functional.cosine_similarity(d_pos, d_neg, dim=0) < -0.5
+    net.__exit__(None, None, None)
+    with torch.no_grad():  # adaptors inert outside `with network:`; same graph-replayed loop without LoRA at all
+        off = generate.denoise_loop(pm, net, sched, lat.clone(), ehs, pooled, tids, num_inference_steps=steps,
+                                    guidance_scale=5.0, scale=0.0, start_noise=1000)
+    assert torch.equal(off, base)
