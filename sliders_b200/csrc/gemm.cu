@@ -42,7 +42,7 @@ constexpr int kBarRegion = 1024;
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // UMMA smem descriptor, high word
 constexpr int kSlab = 32;             // output columns staged per epilogue-warp iteration
 constexpr int kEpiBufBytes = 32 * 64; // [32 rows x 32 cols] bf16
-constexpr int kEpiBytesPerWarp = 2 * kEpiBufBytes;
+constexpr int kEpiBytesPerWarp = 2 * kEpiBufBytes;  // + 2 x [32 cols][r] fp32 of lora_up rows when LoRA is fused (p.up_buf_bytes)
 constexpr int kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
 
 struct GemmParams {
@@ -59,6 +59,9 @@ struct GemmParams {
   int stage_bytes;  // bytes of one smem stage of ONE CTA
   int b_rows;       // W rows staged per CTA per k-block (bn / kCtas)
   int l_rows;       // LoRA-down rows staged per CTA (rt / kCtas)
+  int up_buf_bytes; // per-warp staging of one slab's lora_up rows: 32 * r * 4 (0 without LoRA)
+  int n_fast;       // tile order: 1 = consecutive work units share the A row-tile and walk the N tiles (A is read from
+                    // DRAM once, W stays L2-resident); 0 = M fastest (A re-streamed once per N tile when it exceeds L2)
   int a_mode;       // 0 plain, 1 conv3x3 stride 1, 2 conv3x3 stride 2
   int kb_split;     // k-blocks (per tap) that come from source 0
   int cb_total;     // k-blocks per tap
@@ -90,15 +93,17 @@ __device__ __forceinline__ void add_bf16x16(float* f, const __nv_bfloat16* src) 
 }
 
 template <int R>
-__device__ __forceinline__ void lora_apply(float* f, const float* t, const float* up_rows) {
-  // up_rows: 16 consecutive rows of [N, R] fp32 (same address for the whole warp -> L1 broadcast)
+__device__ __forceinline__ void lora_apply(float* f, const float* t, uint32_t up_rows) {
+  // up_rows: shared-memory address of 16 consecutive rows of [N, R] fp32 (same address for the whole warp: broadcast)
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float4 u0 = __ldg(reinterpret_cast<const float4*>(up_rows + i * R));
-    f[i] += t[0] * u0.x + t[1] * u0.y + t[2] * u0.z + t[3] * u0.w;
+    const uint4 a = ld_shared_v4(up_rows + i * R * 4);
+    f[i] += t[0] * __uint_as_float(a.x) + t[1] * __uint_as_float(a.y) + t[2] * __uint_as_float(a.z) +
+            t[3] * __uint_as_float(a.w);
     if constexpr (R == 8) {
-      const float4 u1 = __ldg(reinterpret_cast<const float4*>(up_rows + i * R + 4));
-      f[i] += t[4] * u1.x + t[5] * u1.y + t[6] * u1.z + t[7] * u1.w;
+      const uint4 b = ld_shared_v4(up_rows + i * R * 4 + 16);
+      f[i] += t[4] * __uint_as_float(b.x) + t[5] * __uint_as_float(b.y) + t[6] * __uint_as_float(b.z) +
+              t[7] * __uint_as_float(b.w);
     }
   }
 }
@@ -177,8 +182,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int t = unit; t < total_tiles; t += num_units) {
-        const int mt = t % p.num_m_tiles;
-        const int nt = t / p.num_m_tiles;
+        const int mt = p.n_fast ? t / p.num_n_tiles : t % p.num_m_tiles;
+        const int nt = p.n_fast ? t % p.num_n_tiles : t / p.num_m_tiles;
         const int m0 = (mt * kCtas + static_cast<int>(cta_rank)) * kBM;
         int b0 = 0, h0 = 0, w0 = 0;
         if (p.a_mode != 0) {
@@ -352,11 +357,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     // per-warp staging buffers (2 x [32 rows x 32 cols] bf16, 64 B rows, 16-byte chunks XOR-swizzled by
     // (row >> 1) & 3): residual tiles arrive here by cp.async with coalesced global reads, results leave from
     // here with coalesced global writes; in between every thread touches only its own row.
-    const uint32_t ebuf = tiles + static_cast<uint32_t>(S) * p.stage_bytes + static_cast<uint32_t>(warp - 2) * kEpiBytesPerWarp;
+    const uint32_t ebuf = tiles + static_cast<uint32_t>(S) * p.stage_bytes +
+                          static_cast<uint32_t>(warp - 2) * (kEpiBytesPerWarp + 2 * p.up_buf_bytes);
+    const uint32_t ubuf0 = ebuf + 2 * kEpiBufBytes;  // 2 x p.up_buf_bytes, same double-buffer parity as ebuf
     int bufsel = 0;
     for (int t = unit; t < total_tiles; t += num_units) {
-      const int mt = t % p.num_m_tiles;
-      const int nt = t / p.num_m_tiles;
+      const int mt = p.n_fast ? t / p.num_n_tiles : t % p.num_m_tiles;
+      const int nt = p.n_fast ? t % p.num_n_tiles : t / p.num_m_tiles;
       const int m_q = (mt * kCtas + static_cast<int>(cta_rank)) * kBM + q * 32;  // first row of this warp
       const int m = m_q + lane;
       const bool row_ok = m < p.M;
@@ -366,17 +373,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       const int my_slabs = (p.debug & 8) ? 0 : ((nslabs - hsel + 1) >> 1);  // slabs hsel, hsel+2, ... (debug 8: skip)
       auto prefetch_resid = [&](int col0, int sw, uint32_t buf) {
         const int cpr = sw >> 3;  // 16-byte chunks per row
-        for (int idx = lane; idx < 32 * cpr; idx += 32) {
-          const int row = idx / cpr;
-          const int ch = idx - row * cpr;
-          const int mr = m_q + row;
-          if (mr < p.M)
-            cp_async_16(buf + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4),
-                        p.resid + static_cast<size_t>(mr) * p.ldr + n_base + col0 + ch * 8);
+        if (has_resid) {
+          for (int idx = lane; idx < 32 * cpr; idx += 32) {
+            const int row = idx / cpr;
+            const int ch = idx - row * cpr;
+            const int mr = m_q + row;
+            if (mr < p.M)
+              cp_async_16(buf + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4),
+                          p.resid + static_cast<size_t>(mr) * p.ldr + n_base + col0 + ch * 8);
+          }
+        }
+        if (has_lora && lane < sw) {
+          // this slab's lora_up rows ([r] fp32 per output column) travel with the residual: the rank-r update then
+          // reads them from shared memory instead of taking an L2 round trip per 16 columns inside the loop
+          const uint32_t ub = ubuf0 + (buf == ebuf ? 0u : static_cast<uint32_t>(p.up_buf_bytes)) + lane * p.lora_r * 4;
+          const float* src = p.lora_up + static_cast<size_t>(n_base + col0 + lane) * p.lora_r;
+          cp_async_16(ub, src);
+          if (p.lora_r == 8) cp_async_16(ub + 16, src + 4);
         }
         cp_async_commit();
       };
-      if (has_resid && my_slabs > 0)
+      const bool staged = has_resid || has_lora;
+      if (staged && my_slabs > 0)
         prefetch_resid(hsel * kSlab, min(kSlab, ncols_valid - hsel * kSlab), ebuf + bufsel * kEpiBufBytes);
       const __nv_bfloat16* rb =
           (p.flags & SB200_EPI_ROWBIAS)
@@ -394,7 +412,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         const int sw = min(kSlab, ncols_valid - col0);
         const uint32_t buf = ebuf + bufsel * kEpiBufBytes;
         const bool more = k + 1 < my_slabs;
-        if (has_resid && more) {
+        if (staged && more) {
           const int ncol0 = col0 + 2 * kSlab;
           prefetch_resid(ncol0, min(kSlab, ncols_valid - ncol0), ebuf + (bufsel ^ 1) * kEpiBufBytes);
         }
@@ -420,8 +438,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (staged && sub == 0) {  // this slab's residual / lora_up rows have landed (the next slab's copy may be in flight)
+            if (more)
+              cp_async_wait<1>();
+            else
+              cp_async_wait<0>();
+            __syncwarp();
+          }
           if (has_lora) {
-            const float* up = p.lora_up + static_cast<size_t>(n) * p.lora_r;
+            const uint32_t up = ubuf0 + static_cast<uint32_t>(bufsel) * p.up_buf_bytes + sub * 16 * p.lora_r * 4;
             if (p.lora_r == 4)
               lora_apply<4>(f, tl, up);
             else
@@ -440,13 +465,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           const uint32_t a0 = buf + lane * 64 + (((2 * sub) ^ swz) << 4);
           const uint32_t a1 = buf + lane * 64 + (((2 * sub + 1) ^ swz) << 4);
           if (has_resid) {
-            if (sub == 0) {  // this slab's residual has landed (the next slab's copy may still be in flight)
-              if (more)
-                cp_async_wait<1>();
-              else
-                cp_async_wait<0>();
-              __syncwarp();
-            }
             const uint4 r0 = ld_shared_v4(a0), r1 = ld_shared_v4(a1);
             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -574,17 +592,28 @@ static bool elect_issue_default() {
   return v;
 }
 
+static bool n_fast_default() {
+  static const bool v = [] {
+    const char* e = getenv("SB200_TILE_ORDER");  // "m" restores the M-fastest order (same-box A/B)
+    return !(e && e[0] == 'm');
+  }();
+  return v;
+}
+
 static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
+  p.n_fast = n_fast_default() ? 1 : 0;
   const bool elect = elect_issue_default() != ((p.debug & 32) != 0);  // debug bit 32 flips the default
   const bool has_lora = p.flags & SB200_EPI_LORA;
   p.b_rows = p.bn / ctas;
   p.l_rows = has_lora ? p.lora_rt / ctas : 0;
   p.stage_bytes = kBM * 128 + p.b_rows * 128 + p.l_rows * 128;
-  int stages = (kSmemBudget - kBarRegion - 1024 - kEpiBytes) / p.stage_bytes;
+  p.up_buf_bytes = has_lora ? kSlab * p.lora_r * 4 : 0;
+  const int epi_bytes = kEpiBytes + kEpiWarps * 2 * p.up_buf_bytes;
+  int stages = (kSmemBudget - kBarRegion - 1024 - epi_bytes) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(SB200_ERR_INVALID, "gemm: tile does not fit shared memory");
   p.stages = stages;
-  const int smem = kBarRegion + 1024 + stages * p.stage_bytes + kEpiBytes;
+  const int smem = kBarRegion + 1024 + stages * p.stage_bytes + epi_bytes;
   if (!ctx->gemm_attr_set) {
     SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));

@@ -571,3 +571,55 @@ def test_full_size_inference_sweep_properties(dev):
         off = generate.denoise_loop(pm, net, sched, lat.clone(), ehs, pooled, tids, num_inference_steps=steps,
                                     guidance_scale=5.0, scale=0.0, start_noise=1000)
     assert torch.equal(off, base)
+
+
+def test_full_sd15_lora_gradients_vs_fp32_oracle(dev):
+    """BASELINE configs 1-2 (SD-1.x text slider, rank 4, 512 px): one grad-carrying `predict_noise` (train_lora.py:
+    263-275) + MSE loss; LoRA gradients of all 150 adaptors vs the fp32 oracle's autograd.  Exercises the
+    attention backward at head dims 40 / 80 / 160 and the 8x8 bottleneck."""
+    from oracle import unet as ounet
+    from sliders_b200 import lora as plora, synthetic, train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    with torch.device(dev):
+        pm = UNet2DConditionModel(UNetConfig.sd15()).to(BF)
+        om = ounet.UNet2DConditionModel(ounet.UNetConfig.sd15())
+    synthetic.init_synthetic_(pm, seed=5)
+    om.load_state_dict({k: v.float() for k, v in pm.state_dict().items()})
+    om.eval().requires_grad_(False)
+    pm.requires_grad_(False)
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+    assert len(net.unet_loras) == 150
+    synthetic.init_lora_nonzero_(net, seed=6, up_std=0.05)
+    net.requires_grad_(True)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 4, 64, 64, generator=g).to(dev, BF)
+    ehs = torch.randn(2, 77, 768, generator=g).to(dev, BF)
+    goal = torch.randn(1, 4, 64, 64, generator=g).to(dev)
+    sched = create_noise_scheduler("ddim")
+    sched.set_timesteps(1000)
+    with net:
+        pred = train_util.predict_noise(pm, sched, 321, lat, ehs, guidance_scale=1.0)
+    torch.nn.functional.mse_loss(pred.float(), goal).backward()
+    torch.cuda.synchronize()
+
+    def call(fp):
+        out = torch.func.functional_call(om, fp, (torch.cat([lat.float()] * 2), 321, ehs.float())).sample
+        u, c = out.chunk(2)
+        ref = u + 1.0 * (c - u)
+        assert rel_rms(pred, ref) < 2.5e-2
+        return torch.nn.functional.mse_loss(ref, goal)
+
+    leaves = _oracle_lora_grads(om, net, 1.0, call)
+    num = den = 0.0
+    for l in net.unet_loras:
+        for got, ref in ((l.lora_down.weight.grad, leaves[l.lora_name][0].grad),
+                         (l.lora_up.weight.grad, leaves[l.lora_name][1].grad)):
+            assert got is not None and torch.isfinite(got).all(), l.lora_name
+            num += (got.float() - ref).pow(2).sum().item()
+            den += ref.pow(2).sum().item()
+    total = (num / den) ** 0.5
+    print(f"SD1.5 LoRA gradient rel-RMS vs fp32 oracle: {total:.4f}")
+    assert total < 6e-2, total
