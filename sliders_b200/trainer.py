@@ -204,12 +204,18 @@ def image_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler
                          latents_low: torch.Tensor, latents_high: torch.Tensor, scale_to_look: float, *,
                          max_denoising_steps: int = 50, timesteps_to: Optional[int] = None, device=None,
                          weight_dtype=torch.bfloat16, seed: Optional[int] = None,
-                         reference_dead_code: bool = False):
+                         reference_dead_code: bool = False, group=None):
     """train_lora-scale-xl.py:178-375 with the image pair already in latent space ([bs,4,h,w], scaled by the VAE
     factor as `get_noisy_image` does, imagesliders/train_util.py:201-235).  Two grad-carrying predictions (+scale on
-    the `high` sample, -scale on the `low` one), two `backward()` calls accumulating into .grad, one optimizer step."""
+    the `high` sample, -scale on the `low` one), two `backward()` calls accumulating into .grad, one optimizer step.
+
+    Under torch.distributed (BASELINE config 4) the two grad-carrying predictions run on rank parity (even ranks: high /
+    +scale, odd ranks: low / -scale) and, when the batch divides, each parity group splits the batch; every rank
+    back-propagates its share of `loss_high + loss_low` and ONE all-reduce of the flat LoRA gradient precedes the
+    identical AdamW step."""
     device = device or unet.device
     criteria = torch.nn.MSELoss()
+    world, rank = _world(group)
     with torch.no_grad():
         noise_scheduler.set_timesteps(max_denoising_steps, device=device)
         optimizer.zero_grad()
@@ -217,6 +223,10 @@ def image_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler
             timesteps_to = torch.randint(1, max_denoising_steps - 1, (1,)).item()       # :193-196
         if seed is None:
             seed = int(torch.randint(0, 2 ** 15, (1,)).item())
+        if world > 1:  # replicas must agree on the step count and on the noise
+            tt = torch.tensor([timesteps_to, seed], device=device)
+            dist.broadcast(tt, src=_global_rank(0, group), group=group)
+            timesteps_to, seed = int(tt[0].item()), int(tt[1].item())
         h, w = latents_low.shape[-2:]
         height, width = h * train_util.VAE_SCALE_FACTOR, w * train_util.VAE_SCALE_FACTOR
         timestep = noise_scheduler.timesteps[timesteps_to]                              # get_noisy_image :224-231
@@ -233,16 +243,34 @@ def image_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler
                                         **_xl_inputs(prompt_pair, prompt_pair.positive, add_time_ids), guidance_scale=1)
             train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy_low,
                                         **_xl_inputs(prompt_pair, prompt_pair.neutral, add_time_ids), guidance_scale=1)
-    losses = []
-    for sign, noisy, which in ((+1.0, noisy_high, prompt_pair.positive), (-1.0, noisy_low, prompt_pair.neutral)):
+    bs = noisy_low.shape[0]
+    groups = world // 2 if world > 1 else 1            # batch shards per sign
+    if world > 1 and (bs % groups != 0 or groups == 0):
+        groups = 1                                      # batch does not divide: one rank per sign, the rest idle
+    losses = [torch.zeros((), device=device), torch.zeros((), device=device)]
+    for i, (sign, noisy, which) in enumerate(((+1.0, noisy_high, prompt_pair.positive),
+                                              (-1.0, noisy_low, prompt_pair.neutral))):
+        lo, hi = 0, bs
+        if world > 1:
+            if rank % 2 != i or rank // 2 >= groups:
+                continue
+            lo, hi = parallel.shard_range(bs, rank // 2, groups)
         network.set_lora_slider(scale=sign * scale_to_look)                             # :311, :343
+        inputs = _xl_inputs(prompt_pair, which, add_time_ids)
+        if (lo, hi) != (0, bs):  # [uncond x bs ; cond x bs] -> this rank's samples of both halves
+            inputs = {k: torch.cat([v[lo:hi], v[bs + lo:bs + hi]]) for k, v in inputs.items()}
         with network:
-            pred = train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy,
-                                               **_xl_inputs(prompt_pair, which, add_time_ids),
+            pred = train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy[lo:hi], **inputs,
                                                guidance_scale=1).to(device, dtype=torch.float32)
-        loss = criteria(pred, noise.to(torch.float32))                                  # :338, :370
-        loss.backward()
-        losses.append(loss.detach())
+        loss = criteria(pred, noise[lo:hi].to(torch.float32))                           # :338, :370
+        # MSE is a mean over the batch: a shard contributes (its mean) / (number of shards)
+        (loss / groups if world > 1 else loss).backward()
+        losses[i] = loss.detach() / (groups if world > 1 else 1)
+    if world > 1:
+        parallel.allreduce_lora_grads([p for g in optimizer.param_groups for p in g["params"]], group=group)
+        both = torch.stack(losses).float()
+        dist.all_reduce(both, group=group)
+        losses = [both[0], both[1]]
     optimizer.step()
     if lr_scheduler is not None:
         lr_scheduler.step()

@@ -363,3 +363,72 @@ def test_text_slider_step_sharded_two_ranks_gloo(tmp_path):
     # rank 1 owns the grad-carrying target prediction (forward + backward), rank 0 the three frozen ones
     assert r0["calls"].count("predict") == 9 and r1["calls"].count("predict") == 3
     assert s["calls"].count("predict") == 12
+
+
+_IMG_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sliders_b200 import trainer, train_util
+world = int(sys.argv[4])
+if world > 1:
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=world)
+
+class Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(5)
+        self.a = torch.nn.Parameter(torch.randn(4, 4, generator=g) * 0.3)
+        self.multiplier, self.lora_scale = 0.0, 1.0
+    def set_lora_slider(self, scale): self.lora_scale = scale
+    def __enter__(self): self.multiplier = self.lora_scale
+    def __exit__(self, *a): self.multiplier = 0.0
+net = Net()
+def predict_noise_xl(unet, sched, t, lat, text_embeddings, add_text_embeddings, add_time_ids, guidance_scale=7.5, **kw):
+    assert text_embeddings.shape[0] == 2 * lat.shape[0] and add_time_ids.shape[0] == 2 * lat.shape[0]
+    e = text_embeddings[lat.shape[0]:].mean(dim=(1, 2))[:, None, None, None]
+    return torch.tanh(lat.float() + e) + net.multiplier * torch.einsum("oc,bchw->bohw", net.a, lat.float())
+train_util.predict_noise_xl = predict_noise_xl
+from sliders_b200.scheduler import create_noise_scheduler
+sched = create_noise_scheduler("ddim")
+g = torch.Generator().manual_seed(1)
+mk = lambda: trainer.PromptEmbedsXL(torch.randn(1, 77, 8, generator=g), torch.randn(1, 4, generator=g))
+unc, pos, neu = mk(), mk(), mk()
+bs = int(sys.argv[6])
+pair = trainer.PromptEmbedsPair(torch.nn.MSELoss(), pos, pos, unc, neu,
+                                trainer.PromptSettings(guidance_scale=1.0, resolution=64, batch_size=bs))
+low = torch.randn(bs, 4, 8, 8, generator=g); high = low + 0.2 * torch.randn(bs, 4, 8, 8, generator=g)
+opt = torch.optim.SGD(net.parameters(), lr=0.1)
+out = []
+for it in range(2):
+    ls = trainer.image_slider_step_xl(None, net, sched, opt, None, pair, low, high, 2.0, timesteps_to=10, seed=3 + it,
+                                      device="cpu", weight_dtype=torch.float32)
+    out.append([float(l) for l in ls])
+torch.save({"a": net.a.detach(), "losses": out}, sys.argv[5])
+if world > 1:
+    dist.destroy_process_group()
+print("ok")
+'''
+
+
+@pytest.mark.parametrize("world,bs", [(2, 1), (4, 2)])
+def test_image_slider_step_sharded_gloo(tmp_path, world, bs):
+    """BASELINE config 4's host logic: the +scale / -scale predictions on rank parity (and the batch split over
+    rank // 2 when it divides) give the single-process weights."""
+    script = tmp_path / "img_worker.py"
+    script.write_text(_IMG_WORKER)
+    port = 33500 + (os.getpid() % 2000) + 7 * world
+    outs = [str(tmp_path / f"o{r}.pt") for r in range(world)]
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), str(world), outs[r], str(bs)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    logs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, logs):
+        assert p.returncode == 0 and "ok" in o, o
+    single = str(tmp_path / "single.pt")
+    p = subprocess.run([sys.executable, str(script), ROOT, str(port + 1), "0", "1", single, str(bs)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    ref = torch.load(single)
+    for o in outs:
+        got = torch.load(o)
+        assert torch.allclose(got["a"], ref["a"], rtol=1e-5, atol=1e-6), (got["a"] - ref["a"]).abs().max()
+        assert all(abs(x - y) < 1e-5 for a, b in zip(got["losses"], ref["losses"]) for x, y in zip(a, b))
