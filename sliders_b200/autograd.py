@@ -157,7 +157,7 @@ def _resnet_fwd(unet, blk, x0, x1, emb_act):
         assert x1 is None
         res = x0
     out = ops.conv3x3(h3, unet._w(blk.conv2), bias=unet._b(blk.conv2), resid=res, lora=unet._lora([blk.conv2]))
-    return out, (blk, x0, x1, emb_act, ws1, h1, h2, ws2, h3)
+    return out, (blk, x0, x1, emb_act, ops.gn_stats(ws1, B, n1.num_groups), h1, h2, ops.gn_stats(ws2, B, n2.num_groups), h3)
 
 
 def _resnet_bwd(unet, grads, rec, d_out, need_dx=True):
@@ -282,7 +282,7 @@ def _transformer_fwd(unet, tr, x, ctx, Sctx, kv_all):
         h = ops.gemm(f, unet._w(ffo), bias=unet._b(ffo), resid=h3, lora=unet._lora([ffo]))
         blocks.append((blk, h1, a1, h2, a2, h3, pre))
     out = ops.gemm(h, unet._w(tr.proj_out), bias=unet._b(tr.proj_out), resid=res, lora=unet._lora([tr.proj_out]))
-    return out.view(B, H, W, C_), (tr, x, ws, hn, blocks, h)
+    return out.view(B, H, W, C_), (tr, x, ops.gn_stats(ws, B, gn.num_groups), hn, blocks, h)
 
 
 def _transformer_bwd(unet, grads, rec, d_out):
@@ -369,8 +369,27 @@ def forward_train(unet, sample, timesteps_f32, ehs, added_cond_kwargs, out_dtype
     ws = ops.gn_ws(B, gn.num_groups, h.device)
     hn = ops.groupnorm(h, *unet._w_norm(gn), gn.num_groups, gn.eps, True, stats_ws=ws)
     out = ops.conv_out(hn, unet._w(unet.conv_out), unet._b(unet.conv_out), out_dtype=out_dtype)
-    tape.append(("out", (h, ws)))
+    tape.append(("out", (h, ops.gn_stats(ws, B, gn.num_groups))))
     return out, tape
+
+
+def slice_tape(obj, lo: int, hi: int, B: int):
+    """The tape restricted to samples [lo, hi) of the batch: every saved activation is batch-major ([B, ...] or a
+    token matrix [B * rows, C]), so a view suffices.  Used to skip samples whose incoming gradient is exactly zero —
+    the unconditional half of a CFG pair at guidance_scale 1 (train_util.py:250-253: d eps / d uncond = 1 - g = 0;
+    every grad-carrying prediction of the trainers is made at guidance 1)."""
+    if torch.is_tensor(obj):
+        if obj.dim() >= 3 and obj.shape[0] == B:
+            return obj[lo:hi]
+        if obj.dim() == 2 and obj.shape[0] % B == 0:
+            rpb = obj.shape[0] // B
+            return obj[lo * rpb:hi * rpb]
+        raise RuntimeError(f"slice_tape: tensor of shape {tuple(obj.shape)} is not batch-major for B={B}")
+    if isinstance(obj, tuple):
+        return tuple(slice_tape(o, lo, hi, B) for o in obj)
+    if isinstance(obj, list):
+        return [slice_tape(o, lo, hi, B) for o in obj]
+    return obj  # modules, ints, None, the scales snapshot
 
 
 def backward(unet, tape, d_eps: torch.Tensor) -> Dict[int, torch.Tensor]:
@@ -456,15 +475,30 @@ class _TrainCapture:
         finally:
             unet._capturing = False
         self.d_out = torch.zeros_like(self.out)
-        self.gb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.gb, pool=self.gf.pool()):
-            by_param = backward(unet, self.tape, self.d_out)
+        self.unet = unet
+        self.bwd = {}  # dead leading samples -> (graph, flat fp32 gradient of every adaptor weight)
+
+    def _capture_backward(self, dead: int):
+        unet = self.unet
+        B = self.out.shape[0]
+        tape = slice_tape(self.tape, dead, B, B) if dead else self.tape
+        d_live = self.d_out[dead:] if dead else self.d_out
+        stream = torch.cuda.Stream(device=self.x.device)
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            backward(unet, tape, d_live)  # warm-up of this variant
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self.gf.pool()):
+            by_param = backward(unet, tape, d_live)
             pieces = []
             for key, (shape, dtype) in zip(self.keys, self.meta):
                 g = by_param.get(key)
                 g = _param_grad(shape, dtype, g) if g is not None else torch.zeros(shape, device=self.x.device, dtype=dtype)
                 pieces.append(g.reshape(-1).to(torch.float32))
-            self.flat = torch.cat(pieces)
+            flat = torch.cat(pieces)
+        self.bwd[dead] = (graph, flat)
 
     def run_forward(self, unet, x, t, ehs, added):
         self.x.copy_(x)
@@ -481,11 +515,14 @@ class _TrainCapture:
         self.pending = True
         return self.out.clone()
 
-    def run_backward(self, d_out):
+    def run_backward(self, d_out, dead: int = 0):
         self.d_out.copy_(d_out)
-        self.gb.replay()
+        if dead not in self.bwd:
+            self._capture_backward(dead)
+        graph, flat_static = self.bwd[dead]
+        graph.replay()
         self.pending = False
-        flat = self.flat.clone()
+        flat = flat_static.clone()
         grads, off = [], 0
         by_dtype = {}
         for shape, dtype in self.meta:
@@ -540,13 +577,18 @@ class _UNetFunction(torch.autograd.Function):
     def backward(fctx, d_out):
         if fctx.tape is None:
             raise RuntimeError("sliders_b200: backward through the same UNet call twice (retain_graph is not supported)")
+        dead = int(getattr(fctx, "zero_rows", 0) or 0)  # leading samples whose incoming gradient is exactly zero
         if fctx.cap is not None:
             with torch.no_grad():
-                grads = fctx.cap.run_backward(d_out)
+                grads = fctx.cap.run_backward(d_out, dead)
             fctx.tape = None
             return (None, None, *grads)
         with torch.no_grad():
-            by_param = backward(fctx.unet, fctx.tape, d_out.contiguous())
+            tape, d_live = fctx.tape, d_out.contiguous()
+            if dead:
+                B = d_out.shape[0]
+                tape, d_live = slice_tape(tape, dead, B, B), d_live[dead:]
+            by_param = backward(fctx.unet, tape, d_live)
         fctx.tape = None  # free the activations
         out = [None, None]
         for key, (shape, dtype) in zip(fctx.keys, fctx.meta):

@@ -260,6 +260,11 @@ def gn_ws(B: int, groups: int, device) -> torch.Tensor:
     return torch.empty(B * groups * 2 * 129, device=device, dtype=torch.float32)
 
 
+def gn_stats(ws: torch.Tensor, B: int, groups: int) -> torch.Tensor:
+    """The [B, groups, 2] (mean, rstd) block `groupnorm` left in its workspace (a view: keeps `ws` alive)."""
+    return ws[B * groups * 2 * GN_STATS_OFFSET:].view(B, groups, 2)
+
+
 def attention_bwd(q, k, v, o, dout, lse, B: int, heads: int, Sq: int, Skv: int, scale: float, head_dim: int,
                   dq: torch.Tensor, dk: Optional[torch.Tensor] = None, dv: Optional[torch.Tensor] = None) -> None:
     """dq (and dk, dv) are 2-D (possibly column-sliced) outputs.  `attn_bwd_prep_kernel` + `attention_bwd_kernel`
@@ -277,7 +282,8 @@ def attention_bwd(q, k, v, o, dout, lse, B: int, heads: int, Sq: int, Skv: int, 
 
 
 def groupnorm_bwd(x0, gamma, beta, groups: int, silu: bool, dy, stats_ws, *, x1=None, add=None) -> torch.Tensor:
-    """Input gradient of `groupnorm` (concat layout [.., C0 + C1]); stats_ws is the forward's workspace."""
+    """Input gradient of `groupnorm` (concat layout [.., C0 + C1]); stats_ws is the forward's workspace, or its
+    (mean, rstd) block as a [B, groups, 2] tensor (`gn_stats` — sliceable along the batch)."""
     shp = x0.shape
     B, C0 = shp[0], shp[-1]
     HW = x0.numel() // (B * C0)
@@ -285,7 +291,8 @@ def groupnorm_bwd(x0, gamma, beta, groups: int, silu: bool, dy, stats_ws, *, x1=
     Cc = C0 + C1
     dx = torch.empty(shp[:-1] + (Cc,), device=x0.device, dtype=BF16)
     ws = gn_ws(B, groups, x0.device)
-    fwd = stats_ws[B * groups * 2 * GN_STATS_OFFSET:]
+    fwd = stats_ws if stats_ws.dim() == 3 else stats_ws[B * groups * 2 * GN_STATS_OFFSET:]
+    assert fwd.is_contiguous()
     lib = _begin()
     _cabi.check(lib.sb200_groupnorm_bwd(
         _ctx(x0), _stream(), _p(x0), x0.stride(-2), C0, _p(x1), x1.stride(-2) if x1 is not None else 0, C1,

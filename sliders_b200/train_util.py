@@ -51,6 +51,11 @@ def _cfg(noise_pred: torch.Tensor, guidance_scale: float) -> torch.Tensor:
         # grad-carrying prediction (train_lora_xl.py:299-322): the combine stays a torch op so autograd links the
         # loss to the UNet node, whose backward is the sb200 backward pass (sliders_b200/autograd.py)
         uncond, text = noise_pred.chunk(2)
+        node = noise_pred.grad_fn
+        if float(guidance_scale) == 1.0 and type(node).__name__.startswith("_UNetFunction"):
+            # d eps / d uncond = 1 - guidance_scale = 0 exactly: tell the UNet node that the first half of its batch
+            # receives a zero gradient, so its backward runs on the conditional samples only
+            node.zero_rows = uncond.shape[0]
         return uncond + guidance_scale * (text - uncond)
     guided, _ = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, out_dtype=noise_pred.dtype)
     return guided

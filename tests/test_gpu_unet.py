@@ -205,6 +205,12 @@ def test_golden_tiny_xl_lora_gradients(dev):
         target = train_util.predict_noise_xl(pm, sched, fx["timestep"], lat, ehs, pooled, tids, guidance_scale=1)
     assert target.requires_grad
     assert rel_rms(target, gg["target"]) < 3e-2
+    # guidance 1: the UNet node was told that its unconditional sample gets a zero gradient (backward runs on the
+    # conditional half only; the golden gradients below are the reference's full-batch autograd)
+    node = target.grad_fn
+    while node is not None and not type(node).__name__.startswith("_UNetFunction"):
+        node = next((f for f, _ in node.next_functions if f is not None), None)
+    assert node is not None and getattr(node, "zero_rows", 0) == 1
     pos, neu, unc = fx["eps_off_g3"].to(dev), fx["eps_off_g1"].to(dev), fx["eps_on_sm2_g3"].to(dev)
     loss = torch.nn.functional.mse_loss(target, neu + 4.0 * (pos - unc))  # prompt_util.py:123-135 (enhance)
     assert abs(loss.item() - gg["loss"].item()) < 0.1 * gg["loss"].item()
