@@ -35,14 +35,19 @@ def t(M, N, K, bn, debug, iters=20, force=0x2000):
     return us, 2.0 * M * N * K / us / 1e6
 
 
-mode = sys.argv[1] if len(sys.argv) > 1 else "single"
-FORCE = 0x1000 if mode == "pair" else 0x2000
-shapes = ((8192, 8192, 8192), (8192, 1280, 1280)) if mode == "pair" else (
-    (8192, 8192, 8192), (8192, 1280, 1280), (8192, 10240, 1280), (8192, 1280, 5120))
-for (M, N, K) in shapes:
-    for bn in ((64, 128, 160, 192, 256) if mode == "pair" else (256, 128)):
-        row = []
-        for debug, name in ((0, "lane0-issue"), (32, "elect-issue"), (0, "lane0 again"), (32, "elect again")):
-            us, tf = t(M, N, K, bn, debug, force=FORCE)
-            row.append(f"{name} {us:8.1f}us {tf:6.0f}TF")
-        print(f"M{M} N{N} K{K} bn{bn}: " + " | ".join(row), flush=True)
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "single"
+    FORCE = 0x1000 if mode == "pair" else 0x2000
+    shapes = ((8192, 8192, 8192), (8192, 1280, 1280)) if mode == "pair" else (
+        (8192, 8192, 8192), (8192, 1280, 1280), (8192, 10240, 1280), (8192, 1280, 5120))
+    for (M, N, K) in shapes:
+        for bn in ((64, 128, 160, 192, 256) if mode == "pair" else (256, 128)):
+            row = []
+            for debug, name in ((0, "lane0-issue"), (32, "elect-issue"), (0, "lane0 again"), (32, "elect again")):
+                us, tf = t(M, N, K, bn, debug, force=FORCE)
+                row.append(f"{name} {us:8.1f}us {tf:6.0f}TF")
+            print(f"M{M} N{N} K{K} bn{bn}: " + " | ".join(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
