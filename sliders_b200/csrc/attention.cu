@@ -42,6 +42,7 @@ struct AttnParams {
   int Sq, Skv;
   int d;           // head dim (multiple of 8)
   int n_kv_tiles;
+  int split_issue;   // 1: Q K^T issued by the TMA warp, P V by the MMA warp (default); 0: both by the MMA warp
   float scale_log2;  // scale * log2(e)
 };
 
@@ -113,6 +114,31 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
   const int n = p.n_kv_tiles;
   const int dsteps = (p.d + 15) >> 4;  // 16-wide k-steps of the QK^T contraction that hold data
 
+  // S_t = Q K_t^T.  Tile j + 1 is issued BEFORE P_j V_j, as soon as the softmax warps have read S_j, so the next S is
+  // ready when they finish tile j.  One thread can issue a tcgen05.mma only every ~176 cycles whatever its size
+  // (tools/micro/umma_bench.cu), and a tile needs 4 + 8 of them, so the two products are issued by DIFFERENT warps
+  // (split_issue): warp 0 issues Q K^T right behind its TMA loads, warp 1 issues P V.  (Measured neutral at d = 64:
+  // 646 vs 643 TFLOP/s — with two CTAs per SM the SM already has two issuing threads; kept because it shortens the
+  // MMA warp's critical path for ND > 1.)
+  const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
+  auto issue_qk = [&](int t) {
+    const int s = t % kStages;
+    const uint32_t ph = (t / kStages) & 1;
+    mbar_wait(bar_kfull + 8 * s, ph);
+    mbar_wait(bar_sfree, (t & 1) ^ 1u);  // softmax finished reading S_{t-1}
+    tc_fence_after();
+    if (elect_one()) {
+      for (int k = 0; k < dsteps; ++k) {
+        const uint32_t off = static_cast<uint32_t>(k >> 2) * kTileBytes + static_cast<uint32_t>(k & 3) * 32;
+        umma_ss(tmem_base + kColS, umma_desc_sw128(sQ + off), umma_desc_sw128(sK + s * kStageBytes + off), idesc_qk,
+                k != 0);
+      }
+      umma_commit(bar_kempty + 8 * s);
+      umma_commit(bar_sfull);
+    }
+    __syncwarp();
+  };
+
   if (warp == 0) {
     // converged warp, one ELECTed lane issues (a `lane == 0` branch makes ptxas wrap every uniform-datapath
     // instruction in an ELECT / BRA.U.ANY retry loop)
@@ -141,36 +167,19 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
           tma_load_4d(sV + s * kStageBytes + i * kTileBytes, &p.tmV, bar_vfull + 8 * s, i * 64, head, j * 128, b);
       }
       __syncwarp();
+      if (p.split_issue) {
+        if (j == 0) mbar_wait(bar_q, 0);
+        issue_qk(j);
+      }
     }
   } else if (warp == 1) {
-    const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
     const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);  // B (= V) is MN-major
     mbar_wait(bar_q, 0);
-    // S_t = Q K_t^T.  Tile j + 1 is issued BEFORE P_j V_j, as soon as the softmax warps have read S_j, so the next S
-    // is ready when they finish tile j (issuing it after P_j V_j left both CTAs of an SM without exp work for about
-    // half of the time: ncu XU pipe 50 %).
-    auto issue_qk = [&](int t) {
-      const int s = t % kStages;
-      const uint32_t ph = (t / kStages) & 1;
-      mbar_wait(bar_kfull + 8 * s, ph);
-      mbar_wait(bar_sfree, (t & 1) ^ 1u);  // softmax finished reading S_{t-1}
-      tc_fence_after();
-      if (elect_one()) {
-        for (int k = 0; k < dsteps; ++k) {
-          const uint32_t off = static_cast<uint32_t>(k >> 2) * kTileBytes + static_cast<uint32_t>(k & 3) * 32;
-          umma_ss(tmem_base + kColS, umma_desc_sw128(sQ + off), umma_desc_sw128(sK + s * kStageBytes + off),
-                  idesc_qk, k != 0);
-        }
-        umma_commit(bar_kempty + 8 * s);
-        umma_commit(bar_sfull);
-      }
-      __syncwarp();
-    };
-    issue_qk(0);
+    if (!p.split_issue) issue_qk(0);
     for (int j = 0; j < n; ++j) {
       const int s = j % kStages;
       const uint32_t ph = (j / kStages) & 1;
-      if (j + 1 < n) issue_qk(j + 1);
+      if (!p.split_issue && j + 1 < n) issue_qk(j + 1);
       // ---- O += P_j V_j
       mbar_wait(bar_vfull + 8 * s, ph);
       mbar_wait(bar_pfull, j & 1);
@@ -422,6 +431,13 @@ extern "C" int sb200_attention(void* handle, void* stream, const void* q, int ld
   p.Skv = Skv;
   p.d = head_dim;
   p.n_kv_tiles = (Skv + 127) / 128;
+  {
+    static const bool split = [] {
+      const char* e = getenv("SB200_ATTN_SPLIT");  // "0" = single issuing warp (same-box A/B)
+      return !(e && e[0] == '0');
+    }();
+    p.split_issue = split ? 1 : 0;
+  }
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Sq + 127) / 128, heads, B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
