@@ -220,6 +220,12 @@ int sb200_upsample2x(void* handle, void* stream, const void* x, void* out, int B
 int sb200_cfg_ddim(void* handle, void* stream, const void* eps2, int eps_is_f32, float g, const void* x,
                    float a_t, float a_prev, void* x_prev, void* eps_out, int out_is_f32, int64_t n);
 
+/* Classifier-free guidance + a scheduler step that is affine in (x, eps): x_prev = cx x + ce eps with host-side
+ * coefficients.  EulerDiscreteScheduler.step (the scheduler the SDXL pipeline of eval-scripts/generate_images_xl.py:358
+ * carries): cx = 1, ce = sigma_next - sigma. */
+int sb200_cfg_step(void* handle, void* stream, const void* eps2, int eps_is_f32, float g, const void* x, float cx,
+                   float ce, void* x_prev, void* eps_out, int out_is_f32, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

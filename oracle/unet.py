@@ -511,7 +511,9 @@ class UNet2DConditionModel(nn.Module):
                 cross_attention_kwargs=None, return_dict: bool = True):
         timesteps = timestep
         if not torch.is_tensor(timesteps):
-            timesteps = torch.tensor([timesteps], dtype=torch.int64, device=sample.device)
+            # diffusers: python floats become float64 tensors, ints int64 (Euler's linspace grid is fractional)
+            timesteps = torch.tensor([timesteps], dtype=torch.float64 if isinstance(timesteps, float) else torch.int64,
+                                     device=sample.device)
         elif timesteps.dim() == 0:
             timesteps = timesteps[None].to(sample.device)
         timesteps = timesteps.expand(sample.shape[0])

@@ -270,9 +270,12 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 // ------------------------------------------------------------------------------------------------
 template <typename TE, typename TO>
 __global__ void cfg_ddim_kernel(const TE* __restrict__ eps2, float g, const TO* __restrict__ x, float a_t,
-                                float a_prev, TO* __restrict__ x_prev, TO* __restrict__ eps_out, int64_t n) {
-  const float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t);
-  const float pa = sqrtf(a_prev), pb = sqrtf(1.f - a_prev);
+                                float a_prev, TO* __restrict__ x_prev, TO* __restrict__ eps_out, int64_t n,
+                                int affine) {
+  // affine: (a_t, a_prev) are the coefficients (cx, ce) of x_prev = cx x + ce eps (Euler-discrete step: cx = 1,
+  // ce = sigma_next - sigma); otherwise the DDIM update from the two alpha-bar values
+  const float sa = affine ? 1.f : sqrtf(a_t), sb = affine ? 0.f : sqrtf(1.f - a_t);
+  const float pa = affine ? a_t : sqrtf(a_prev), pb = affine ? a_prev : sqrtf(1.f - a_prev);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float eu = static_cast<float>(eps2[i]);
@@ -404,9 +407,23 @@ extern "C" int sb200_upsample2x(void* handle, void* stream, const void* x, void*
   return 0;
 }
 
+static int launch_cfg(void* handle, void* stream, const void* eps2, int eps_is_f32, float g, const void* x,
+                      float a_t, float a_prev, void* x_prev, void* eps_out, int out_is_f32, int64_t n, int affine);
+
 extern "C" int sb200_cfg_ddim(void* handle, void* stream, const void* eps2, int eps_is_f32, float g,
                               const void* x, float a_t, float a_prev, void* x_prev, void* eps_out,
                               int out_is_f32, int64_t n) {
+  return launch_cfg(handle, stream, eps2, eps_is_f32, g, x, a_t, a_prev, x_prev, eps_out, out_is_f32, n, 0);
+}
+
+extern "C" int sb200_cfg_step(void* handle, void* stream, const void* eps2, int eps_is_f32, float g,
+                              const void* x, float cx, float ce, void* x_prev, void* eps_out, int out_is_f32,
+                              int64_t n) {
+  return launch_cfg(handle, stream, eps2, eps_is_f32, g, x, cx, ce, x_prev, eps_out, out_is_f32, n, 1);
+}
+
+static int launch_cfg(void* handle, void* stream, const void* eps2, int eps_is_f32, float g, const void* x,
+                      float a_t, float a_prev, void* x_prev, void* eps_out, int out_is_f32, int64_t n, int affine) {
   pdl_hint() = true;
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx && eps2 && n > 0, "cfg_ddim: bad arguments");
@@ -418,7 +435,8 @@ extern "C" int sb200_cfg_ddim(void* handle, void* stream, const void* eps2, int 
 #define SB200_LAUNCH_CFG(TE, TO)                                                                     \
   cfg_ddim_kernel<TE, TO><<<blocks, 256, 0, s>>>(static_cast<const TE*>(eps2), g,                    \
                                                  static_cast<const TO*>(x), a_t, a_prev,             \
-                                                 static_cast<TO*>(x_prev), static_cast<TO*>(eps_out), n)
+                                                 static_cast<TO*>(x_prev), static_cast<TO*>(eps_out), n, \
+                                                 affine)
   if (eps_is_f32 && out_is_f32)
     SB200_LAUNCH_CFG(float, float);
   else if (eps_is_f32 && !out_is_f32)

@@ -43,6 +43,10 @@ def denoise_loop(unet, network, scheduler, latents: torch.Tensor, prompt_embeds:
             a_t, a_prev = scheduler._alphas_for(t)
             _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), a_t, a_prev,
                                       out_dtype=latents.dtype)
+        elif hasattr(scheduler, "_step_coeffs"):  # sliders_b200 EulerDiscreteScheduler: x' = cx x + ce eps
+            cx, ce = scheduler._step_coeffs(t)
+            _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), cx, ce,
+                                      out_dtype=latents.dtype, affine=True)
         else:
             guided, _ = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, out_dtype=noise_pred.dtype)
             latents = scheduler.step(guided, t, latents, return_dict=False)[0]

@@ -225,9 +225,10 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
 
 
 def cfg_ddim(eps2: torch.Tensor, guidance: float, x: Optional[torch.Tensor] = None, a_t: float = 1.0,
-             a_prev: float = 1.0, out_dtype=None, single: bool = False):
+             a_prev: float = 1.0, out_dtype=None, single: bool = False, affine: bool = False):
     """eps2 = [uncond batch ; cond batch] (contiguous).  Returns (guided_eps, x_prev or None).
-    single=True: eps2 is one already-guided eps batch and guidance must be 0 (plain DDIM step)."""
+    single=True: eps2 is one already-guided eps batch and guidance must be 0 (plain DDIM step).
+    affine=True: (a_t, a_prev) are the coefficients (cx, ce) of x_prev = cx x + ce eps (`sb200_cfg_step`)."""
     if single:
         assert guidance == 0.0
         n = eps2.numel()
@@ -243,7 +244,8 @@ def cfg_ddim(eps2: torch.Tensor, guidance: float, x: Optional[torch.Tensor] = No
     if x is not None and x.dtype != out_dtype:
         x = x.to(out_dtype)
     lib = _begin()
-    _cabi.check(lib.sb200_cfg_ddim(_ctx(eps2), _stream(), _p(eps2), int(eps2.dtype == torch.float32),
+    fn = lib.sb200_cfg_step if affine else lib.sb200_cfg_ddim
+    _cabi.check(fn(_ctx(eps2), _stream(), _p(eps2), int(eps2.dtype == torch.float32),
                                    float(guidance), _p(x), float(a_t), float(a_prev), _p(x_prev), _p(eps_out),
                                    int(out_dtype == torch.float32), n))
     _count()

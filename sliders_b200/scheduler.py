@@ -106,11 +106,103 @@ class DDIMScheduler:
         return self.config.num_train_timesteps
 
 
-def create_noise_scheduler(scheduler_name: str = "ddim", prediction_type: str = "epsilon") -> DDIMScheduler:
-    """model_util.create_noise_scheduler (model_util.py:230-278); only the DDIM branch is on the hot path."""
+class EulerDiscreteScheduler:
+    """diffusers' `EulerDiscreteScheduler` (epsilon prediction, linear interpolation, s_churn = 0) — the scheduler the
+    SDXL pipeline carries through eval-scripts/generate_images_xl.py (:267 set_timesteps, :334 scale_model_input,
+    :358 step); defaults are the stabilityai/stable-diffusion-xl-base-1.0 scheduler config.  Coefficients stay on the
+    host; on CUDA tensors `step` is one `cfg_ddim_kernel` launch in its affine mode (x_next = x + (sigma' - sigma) eps),
+    and `generate.denoise_loop` fuses the guidance into the same launch through `_step_coeffs`."""
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 beta_schedule: str = "scaled_linear", prediction_type: str = "epsilon",
+                 interpolation_type: str = "linear", use_karras_sigmas: bool = False,
+                 timestep_spacing: str = "leading", steps_offset: int = 1):
+        if beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        elif beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        else:
+            raise NotImplementedError(beta_schedule)
+        if prediction_type != "epsilon" or interpolation_type != "linear" or use_karras_sigmas:
+            raise NotImplementedError("EulerDiscreteScheduler: epsilon prediction, linear interpolation, no Karras sigmas")
+        if timestep_spacing not in ("linspace", "leading", "trailing"):
+            raise ValueError(f"timestep_spacing {timestep_spacing}")
+        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                                      beta_schedule=beta_schedule, prediction_type=prediction_type,
+                                      timestep_spacing=timestep_spacing, steps_offset=steps_offset)
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self._train_sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
+        self.num_inference_steps: Optional[int] = None
+        self._set(np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=float)[::-1].copy(),
+                  self._train_sigmas[::-1].copy(), None)
+
+    def _set(self, timesteps: np.ndarray, sigmas: np.ndarray, device):
+        sig = np.concatenate([sigmas, [0.0]]).astype(np.float32)
+        self.sigmas = torch.from_numpy(sig).to(device)
+        self.timesteps = torch.from_numpy(timesteps).to(device)
+        self.timesteps_host = [float(v) for v in timesteps]   # host mirrors: no device read-back inside the loops
+        self._sigmas_host = [float(v) for v in sig]
+
+    @property
+    def init_noise_sigma(self) -> float:
+        m = max(self._sigmas_host)
+        return m if self.config.timestep_spacing in ("linspace", "trailing") else (m * m + 1.0) ** 0.5
+
+    def set_timesteps(self, num_inference_steps: int, device: Union[str, torch.device, None] = None):
+        T = self.config.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        sp = self.config.timestep_spacing
+        if sp == "linspace":
+            timesteps = np.linspace(0, T - 1, num_inference_steps, dtype=float)[::-1].copy()
+        elif sp == "leading":
+            timesteps = (np.arange(0, num_inference_steps) * (T // num_inference_steps)).round()[::-1].copy().astype(float)
+            timesteps += self.config.steps_offset
+        else:
+            timesteps = (np.arange(T, 0, -T / num_inference_steps)).round().copy().astype(float) - 1
+        sigmas = np.interp(timesteps, np.arange(0, len(self._train_sigmas)), self._train_sigmas)
+        self._set(timesteps, sigmas, device)
+
+    def _index(self, timestep) -> int:
+        return self.timesteps_host.index(float(timestep))
+
+    def _step_coeffs(self, timestep) -> tuple:
+        """(cx, ce) of x_next = cx x + ce eps."""
+        i = self._index(timestep)
+        return 1.0, self._sigmas_host[i + 1] - self._sigmas_host[i]
+
+    def scale_model_input(self, sample: torch.Tensor, timestep) -> torch.Tensor:
+        sigma = self._sigmas_host[self._index(timestep)]
+        return sample / ((sigma * sigma + 1.0) ** 0.5)
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True, **unused):
+        if self.num_inference_steps is None:
+            raise ValueError("call set_timesteps first")
+        cx, ce = self._step_coeffs(timestep)
+        if model_output.is_cuda:
+            out_dtype = sample.dtype if sample.dtype in (torch.float32, torch.bfloat16) else torch.float32
+            _, prev = ops.cfg_ddim(model_output.contiguous(), 0.0, sample.contiguous(), cx, ce, out_dtype=out_dtype,
+                                   single=True, affine=True)
+            prev = prev.to(sample.dtype)
+        else:  # host tensors (scheduler unit tests); not a model path
+            prev = cx * sample + ce * model_output
+        if not return_dict:
+            return (prev,)
+        return DDIMSchedulerOutput(prev_sample=prev)
+
+    def __len__(self):
+        return self.config.num_train_timesteps
+
+
+def create_noise_scheduler(scheduler_name: str = "ddim", prediction_type: str = "epsilon"):
+    """model_util.create_noise_scheduler (model_util.py:230-278): the DDIM branch (the shipped configs' choice) plus
+    "euler" for the eval loop (the reference's factory itself offers ddim / ddpm / lms / euler_a)."""
     name = scheduler_name.lower().replace(" ", "_")
+    if name == "euler":
+        return EulerDiscreteScheduler(prediction_type=prediction_type)
     if name != "ddim":
         raise NotImplementedError(f"scheduler {scheduler_name}: sliders_b200 restates DDIM (the shipped configs' "
-                                  "choice, data/config-xl.yaml); DDPM/LMS/Euler-a are SURVEY.md §8f rank 3")
+                                  "choice, data/config-xl.yaml) and EulerDiscrete; DDPM/LMS/Euler-a are stochastic or "
+                                  "multistep samplers off the measured path (SURVEY.md §8f rank 3)")
     return DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
                          num_train_timesteps=1000, clip_sample=False, prediction_type=prediction_type)

@@ -629,3 +629,59 @@ def test_full_sd15_lora_gradients_vs_fp32_oracle(dev):
     total = (num / den) ** 0.5
     print(f"SD1.5 LoRA gradient rel-RMS vs fp32 oracle: {total:.4f}")
     assert total < 6e-2, total
+
+
+def test_euler_denoise_loop_matches_oracle(dev):
+    """The eval loop of generate_images_xl.py:325-364 with the scheduler the SDXL pipeline ships (EulerDiscrete, leading
+    spacing, offset 1): 5 steps, guidance 5, slider 1.5 on the tiny SDXL-topology model vs the fp32 oracle UNet driven
+    by oracle/euler.py; the guidance + Euler update runs in the affine mode of `cfg_ddim_kernel`."""
+    import copy
+
+    from oracle import euler as oeuler
+    from oracle import unet as ounet
+    from sliders_b200 import generate, synthetic
+    from sliders_b200.scheduler import create_noise_scheduler
+
+    fx = torch.load(os.path.join(GOLDEN, "tiny_xl.pt"))
+    pm, net = build_product(fx, dev)
+    om = ounet.UNet2DConditionModel(ounet.UNetConfig.tiny_xl())
+    synthetic.init_synthetic_(om, seed=fx["weight_seed"])
+    om.eval()
+    slider = 1.5
+    mods = {("lora_unet_" + n.replace(".", "_")): m for n, m in om.named_modules()}
+    sd = {k: v.float().cpu() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        for l in net.unet_loras:
+            up, down = sd[l.lora_name + ".lora_up.weight"], sd[l.lora_name + ".lora_down.weight"]
+            delta = torch.einsum("or,rikl->oikl", up[:, :, 0, 0], down) if down.dim() == 4 else up @ down
+            mods[l.lora_name].weight.add_(delta * (slider * l.scale))
+    steps, gs = 5, 5.0
+    sch = oeuler.EulerDiscreteScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                        timestep_spacing="leading", steps_offset=1)
+    sch.set_timesteps(steps)
+    g = torch.Generator().manual_seed(11)
+    lat = torch.randn(2, 4, 32, 32, generator=g) * float(sch.init_noise_sigma)
+    ehs = fx["text_embeddings"].repeat_interleave(2, dim=0)
+    pooled = fx["add_text_embeddings"].repeat_interleave(2, dim=0)
+    tids = fx["add_time_ids"].repeat_interleave(2, dim=0)
+    x = lat.clone()
+    with torch.no_grad():
+        for t in sch.timesteps:
+            xin = sch.scale_model_input(torch.cat([x] * 2), float(t))
+            out = om(xin, float(t), ehs, added_cond_kwargs={"text_embeds": pooled, "time_ids": tids}).sample
+            u, c = out.chunk(2)
+            x = sch.step(u + gs * (c - u), float(t), x).prev_sample
+    psch = create_noise_scheduler("euler")
+    psch.set_timesteps(steps)  # init_noise_sigma refers to the current sigma grid (the pipeline sets timesteps first)
+    assert abs(float(psch.init_noise_sigma) - float(sch.init_noise_sigma)) < 1e-3, (psch.init_noise_sigma, sch.init_noise_sigma)
+    got = generate.denoise_loop(pm, net, psch, lat.to(dev), ehs.to(dev), pooled.to(dev), tids.to(dev),
+                                num_inference_steps=steps, guidance_scale=gs, scale=slider, start_noise=1000)
+    r = rel_rms(got, x)
+    print(f"euler loop rel-RMS {r:.4f}")
+    assert r < 6e-2, r  # five guided steps (g = 5) accumulate the per-step bf16 error
+    # scheduler.step alone on device tensors == the host formula
+    e = torch.randn(2, 4, 32, 32, generator=g)
+    t0 = psch.timesteps_host[1]
+    dev_step = psch.step(e.to(dev), t0, lat.to(dev)).prev_sample
+    r2 = rel_rms(dev_step, sch.step(e, t0, lat).prev_sample)
+    assert r2 < 1e-5, r2

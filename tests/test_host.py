@@ -432,3 +432,26 @@ def test_image_slider_step_sharded_gloo(tmp_path, world, bs):
         got = torch.load(o)
         assert torch.allclose(got["a"], ref["a"], rtol=1e-5, atol=1e-6), (got["a"] - ref["a"]).abs().max()
         assert all(abs(x - y) < 1e-5 for a, b in zip(got["losses"], ref["losses"]) for x, y in zip(a, b))
+
+
+def test_euler_scheduler_matches_oracle_restatement():
+    """sliders_b200.scheduler.EulerDiscreteScheduler (eval loop, generate_images_xl.py:267-358) against oracle/euler.py."""
+    from oracle import euler as oeuler
+    from sliders_b200 import scheduler as psched
+
+    for spacing, offset in (("leading", 1), ("linspace", 0), ("trailing", 0)):
+        a = psched.EulerDiscreteScheduler(timestep_spacing=spacing, steps_offset=offset)
+        b = oeuler.EulerDiscreteScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                          timestep_spacing=spacing, steps_offset=offset)
+        assert abs(float(a.init_noise_sigma) - float(b.init_noise_sigma)) < 1e-4
+        for n in (50, 30, 7):
+            a.set_timesteps(n)
+            b.set_timesteps(n)
+            assert torch.equal(a.timesteps, b.timesteps) and torch.allclose(a.sigmas, b.sigmas)
+            g = torch.Generator().manual_seed(n)
+            x = torch.randn(2, 4, 8, 8, generator=g) * float(a.init_noise_sigma)
+            for t in a.timesteps_host[:4] + a.timesteps_host[-2:]:
+                e = torch.randn(2, 4, 8, 8, generator=g)
+                assert torch.allclose(a.scale_model_input(x, t), b.scale_model_input(x, t), atol=1e-6)
+                assert torch.allclose(a.step(e, t, x).prev_sample, b.step(e, t, x).prev_sample, atol=1e-5)
+    assert isinstance(psched.create_noise_scheduler("euler"), psched.EulerDiscreteScheduler)

@@ -244,3 +244,38 @@ def test_reference_state_dict_keys_match_ours():
                 assert list(a.state_dict().keys()) == list(b.state_dict().keys()), method
                 # re-create fresh models: injection swaps the leaf forwards
                 mo, mp = ounet.UNet2DConditionModel(cfg_o), PU(cfg_p)
+
+
+def test_euler_discrete_known_answers_and_ddim_equivalence():
+    """oracle/euler.py: sigma known answers for the SD betas (sigma_max 14.6146, sigma_min 0.0292), the SDXL config's
+    timestep grid (leading, offset 1: 981, 961, ..., 1 for 50 steps) and init_noise_sigma, and the exact
+    correspondence with DDIM (eta 0): on a shared integer grid x_euler = sqrt(1 + sigma^2) * x_ddim at every step."""
+    from oracle import ddim as oddim
+    from oracle import euler as oeuler
+
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    e = oeuler.EulerDiscreteScheduler(timestep_spacing="leading", steps_offset=1, **kw)
+    assert abs(float(e.sigmas.max()) - 14.6146) < 1e-3 and abs(float(e.sigmas[-2]) - 0.0292) < 1e-4
+    assert abs(float(e.init_noise_sigma) - (14.6146 ** 2 + 1) ** 0.5) < 1e-3
+    e.set_timesteps(50)
+    assert [float(t) for t in e.timesteps[:3]] == [981.0, 961.0, 941.0] and float(e.timesteps[-1]) == 1.0
+    assert float(e.sigmas[-1]) == 0.0 and len(e.sigmas) == 51
+    lin = oeuler.EulerDiscreteScheduler(timestep_spacing="linspace", **kw)
+    assert abs(float(lin.init_noise_sigma) - 14.6146) < 1e-3
+    # equivalence with DDIM on the same (integer, leading, offset 0) grid
+    n = 20
+    e0 = oeuler.EulerDiscreteScheduler(timestep_spacing="leading", steps_offset=0, **kw)
+    e0.set_timesteps(n)
+    d = oddim.DDIMScheduler(clip_sample=False, **kw)
+    d.set_timesteps(n)
+    assert [int(t) for t in d.timesteps] == [int(t) for t in e0.timesteps]
+    g = torch.Generator().manual_seed(0)
+    x_vp = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64)
+    x_ve = x_vp * (float(e0.sigmas[0]) ** 2 + 1) ** 0.5
+    for i, t in enumerate(d.timesteps):
+        eps = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64)
+        assert torch.allclose(e0.scale_model_input(x_ve, float(t)), x_vp, rtol=1e-4, atol=1e-5)
+        x_vp = d.step(eps, int(t), x_vp).prev_sample
+        x_ve = e0.step(eps, float(t), x_ve).prev_sample
+        s_next = float(e0.sigmas[i + 1])
+        assert torch.allclose(x_ve, x_vp * (s_next ** 2 + 1) ** 0.5, rtol=2e-4, atol=2e-4)
