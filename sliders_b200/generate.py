@@ -43,7 +43,7 @@ def denoise_loop(unet, network, scheduler, latents: torch.Tensor, prompt_embeds:
             a_t, a_prev = scheduler._alphas_for(t)
             _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), a_t, a_prev,
                                       out_dtype=latents.dtype)
-        elif hasattr(scheduler, "_step_coeffs"):  # sliders_b200 EulerDiscreteScheduler: x' = cx x + ce eps
+        elif getattr(scheduler, "affine_step", False):  # sliders_b200 EulerDiscreteScheduler: x' = cx x + ce eps
             cx, ce = scheduler._step_coeffs(t)
             _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), cx, ce,
                                       out_dtype=latents.dtype, affine=True)

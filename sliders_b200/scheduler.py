@@ -113,6 +113,7 @@ class EulerDiscreteScheduler:
     host; on CUDA tensors `step` is one `cfg_ddim_kernel` launch in its affine mode (x_next = x + (sigma' - sigma) eps),
     and `generate.denoise_loop` fuses the guidance into the same launch through `_step_coeffs`."""
     order = 1
+    affine_step = True  # x_next = cx x + ce eps with host-side (cx, ce): eligible for the fused guidance + step kernel
 
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
                  beta_schedule: str = "scaled_linear", prediction_type: str = "epsilon",
@@ -194,15 +195,71 @@ class EulerDiscreteScheduler:
         return self.config.num_train_timesteps
 
 
+class LMSDiscreteScheduler(EulerDiscreteScheduler):
+    """diffusers' `LMSDiscreteScheduler` as eval-scripts/generate_images_sd1.py:51 builds it (scaled_linear betas
+    0.00085..0.012, 1000 train steps; linspace timesteps) and drives it (:169-192): linear multistep (order 4) on the
+    same sigma grid as Euler.  x_next = x + sum_k c_k d_{i-k} with d = eps (epsilon prediction) and c_k the integral of
+    the k-th Lagrange basis polynomial over [sigma_i, sigma_{i+1}] (scipy.integrate.quad, epsrel 1e-4, as diffusers).
+    The combine is a 4-term linear combination of [N,4,64,64] latents: plain torch ops on whatever device they live on."""
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 beta_schedule: str = "scaled_linear", prediction_type: str = "epsilon",
+                 timestep_spacing: str = "linspace", steps_offset: int = 0):
+        # (the class attribute `affine_step = False` below keeps generate.denoise_loop on its generic scheduler.step branch)
+        super().__init__(num_train_timesteps, beta_start, beta_end, beta_schedule, prediction_type, "linear", False,
+                         timestep_spacing, steps_offset)
+        self.derivatives = []
+
+    def set_timesteps(self, num_inference_steps: int, device: Union[str, torch.device, None] = None):
+        super().set_timesteps(num_inference_steps, device)
+        self.derivatives = []
+
+    def get_lms_coefficient(self, order: int, t: int, current_order: int) -> float:
+        from scipy import integrate
+
+        sig = self._sigmas_host
+
+        def lms_derivative(tau):
+            prod = 1.0
+            for k in range(order):
+                if current_order == k:
+                    continue
+                prod *= (tau - sig[t - k]) / (sig[t - current_order] - sig[t - k])
+            return prod
+
+        return integrate.quad(lms_derivative, sig[t], sig[t + 1], epsrel=1e-4)[0]
+
+    affine_step = False  # multistep: not an affine function of (x, eps) alone
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, order: int = 4,
+             return_dict: bool = True, **unused):
+        if self.num_inference_steps is None:
+            raise ValueError("call set_timesteps first")
+        i = self._index(timestep)
+        sigma = self._sigmas_host[i]
+        pred_original_sample = sample - sigma * model_output
+        self.derivatives.append((sample - pred_original_sample) / sigma)
+        if len(self.derivatives) > order:
+            self.derivatives.pop(0)
+        order = min(i + 1, order)
+        coeffs = [self.get_lms_coefficient(order, i, k) for k in range(order)]
+        prev = sample + sum(c * d for c, d in zip(coeffs, reversed(self.derivatives)))
+        if not return_dict:
+            return (prev,)
+        return DDIMSchedulerOutput(prev_sample=prev)
+
+
 def create_noise_scheduler(scheduler_name: str = "ddim", prediction_type: str = "epsilon"):
     """model_util.create_noise_scheduler (model_util.py:230-278): the DDIM branch (the shipped configs' choice) plus
     "euler" for the eval loop (the reference's factory itself offers ddim / ddpm / lms / euler_a)."""
     name = scheduler_name.lower().replace(" ", "_")
     if name == "euler":
         return EulerDiscreteScheduler(prediction_type=prediction_type)
+    if name == "lms":  # model_util.py:255-262
+        return LMSDiscreteScheduler(prediction_type=prediction_type)
     if name != "ddim":
         raise NotImplementedError(f"scheduler {scheduler_name}: sliders_b200 restates DDIM (the shipped configs' "
-                                  "choice, data/config-xl.yaml) and EulerDiscrete; DDPM/LMS/Euler-a are stochastic or "
-                                  "multistep samplers off the measured path (SURVEY.md §8f rank 3)")
+                                  "choice, data/config-xl.yaml), EulerDiscrete and LMSDiscrete; DDPM / Euler-a are "
+                                  "stochastic samplers off the measured path (SURVEY.md §8f rank 3)")
     return DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
                          num_train_timesteps=1000, clip_sample=False, prediction_type=prediction_type)

@@ -455,3 +455,26 @@ def test_euler_scheduler_matches_oracle_restatement():
                 assert torch.allclose(a.scale_model_input(x, t), b.scale_model_input(x, t), atol=1e-6)
                 assert torch.allclose(a.step(e, t, x).prev_sample, b.step(e, t, x).prev_sample, atol=1e-5)
     assert isinstance(psched.create_noise_scheduler("euler"), psched.EulerDiscreteScheduler)
+
+
+def test_lms_scheduler_matches_oracle_restatement():
+    """sliders_b200.scheduler.LMSDiscreteScheduler (eval-scripts/generate_images_sd1.py:51,169-192) against oracle/lms.py
+    over a whole 12-step trajectory (the multistep history makes every step depend on the previous ones)."""
+    from oracle import lms as olms
+    from sliders_b200 import scheduler as psched
+
+    a = psched.create_noise_scheduler("lms")
+    b = olms.LMSDiscreteScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    assert isinstance(a, psched.LMSDiscreteScheduler) and not a.affine_step
+    a.set_timesteps(12)
+    b.set_timesteps(12)
+    assert torch.equal(a.timesteps, b.timesteps) and torch.allclose(a.sigmas, b.sigmas)
+    assert abs(float(a.init_noise_sigma) - float(b.init_noise_sigma)) < 1e-4
+    g = torch.Generator().manual_seed(2)
+    xa = xb = torch.randn(2, 4, 8, 8, generator=g) * float(a.init_noise_sigma)
+    for t in a.timesteps_host:
+        e = torch.randn(2, 4, 8, 8, generator=g)
+        assert torch.allclose(a.scale_model_input(xa, t), b.scale_model_input(xb, t), atol=1e-5)
+        xa = a.step(e, t, xa).prev_sample
+        xb = b.step(e, t, xb).prev_sample
+        assert torch.allclose(xa, xb, rtol=1e-4, atol=1e-4)

@@ -279,3 +279,40 @@ def test_euler_discrete_known_answers_and_ddim_equivalence():
         x_ve = e0.step(eps, float(t), x_ve).prev_sample
         s_next = float(e0.sigmas[i + 1])
         assert torch.allclose(x_ve, x_vp * (s_next ** 2 + 1) ** 0.5, rtol=2e-4, atol=2e-4)
+
+
+def test_lms_discrete_properties():
+    """oracle/lms.py: first step == Euler step; coefficients sum to d sigma; a cubic-in-sigma derivative is integrated
+    exactly from the fourth step on (order-4 Adams-Bashforth on a non-uniform grid)."""
+    from oracle import euler as oeuler
+    from oracle import lms as olms
+
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    l = olms.LMSDiscreteScheduler(**kw)
+    e = oeuler.EulerDiscreteScheduler(timestep_spacing="linspace", **kw)
+    assert abs(float(l.init_noise_sigma) - 14.6146) < 1e-3
+    l.set_timesteps(30)
+    e.set_timesteps(30)
+    assert torch.equal(l.timesteps, e.timesteps) and torch.equal(l.sigmas, e.sigmas)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64) * 14.6
+    eps = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64)
+    t0 = float(l.timesteps[0])
+    assert torch.allclose(l.step(eps, t0, x).prev_sample, e.step(eps, t0, x).prev_sample, rtol=1e-6, atol=1e-6)
+    for i in (1, 2, 5, 20):
+        order = min(i + 1, 4)
+        cs = [l.get_lms_coefficient(order, i, k) for k in range(order)]
+        assert abs(sum(cs) - float(l.sigmas[i + 1] - l.sigmas[i])) < 1e-4 * abs(float(l.sigmas[i]))
+    # exactness for cubic derivatives: d(sigma) = a + b s + c s^2 + d s^3, x(s) = integral
+    l.set_timesteps(30)
+    a, b, c, d3 = 0.3, -0.2, 0.05, -0.004
+    f = lambda s: a + b * s + c * s ** 2 + d3 * s ** 3
+    F = lambda s: a * s + b * s ** 2 / 2 + c * s ** 3 / 3 + d3 * s ** 4 / 4
+    x = torch.tensor([F(float(l.sigmas[0]))], dtype=torch.float64)
+    for i, t in enumerate(l.timesteps[:8]):
+        s = float(l.sigmas[i])
+        eps = torch.tensor([f(s)], dtype=torch.float64)   # derivative == eps for epsilon prediction
+        x_next = l.step(eps, float(t), x).prev_sample
+        if i >= 3:
+            assert abs(float(x_next) - F(float(l.sigmas[i + 1]))) < 2e-3, i
+        x = torch.tensor([F(float(l.sigmas[i + 1]))], dtype=torch.float64)  # restart from the exact value
