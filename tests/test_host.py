@@ -478,3 +478,40 @@ def test_lms_scheduler_matches_oracle_restatement():
         xa = a.step(e, t, xa).prev_sample
         xb = b.step(e, t, xb).prev_sample
         assert torch.allclose(xa, xb, rtol=1e-4, atol=1e-4)
+
+
+def test_io_unet_and_slider_ingestion(tmp_path):
+    """sliders_b200.io: an HF-style UNet state dict (safetensors) and slider checkpoints written by the reference-style
+    `save_weights` load back bit for bit; mismatching files fail loudly."""
+    from safetensors.torch import save_file
+
+    from oracle import unet as ounet
+    from sliders_b200 import io as sio, lora as plora, synthetic
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    cfg = UNetConfig.from_dict(ounet.UNetConfig.tiny_xl().__dict__)
+    src = UNet2DConditionModel(cfg)
+    synthetic.init_synthetic_(src, seed=3)
+    f = str(tmp_path / "diffusion_pytorch_model.safetensors")
+    save_file({k: v.contiguous() for k, v in src.state_dict().items()}, f)
+    got = sio.load_unet(cfg, f, dtype=torch.float32)
+    for (k, a), (_, b) in zip(src.state_dict().items(), got.state_dict().items()):
+        assert torch.equal(a, b), k
+    with pytest.raises(RuntimeError, match="not a UNet2DConditionModel state dict"):
+        sio.load_unet(UNetConfig.from_dict(ounet.UNetConfig.tiny_sd().__dict__), f)
+    net = plora.LoRANetwork(src, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn")
+    synthetic.init_lora_nonzero_(net, seed=4, up_std=0.05)
+    for ext in (".pt", ".safetensors"):
+        ck = str(tmp_path / ("slider" + ext))
+        net.save_weights(ck, dtype=torch.bfloat16)
+        other = UNet2DConditionModel(cfg)
+        net2 = plora.LoRANetwork(other, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn")
+        sio.load_slider(net2, ck)
+        for (k, a), (_, b) in zip(net.state_dict().items(), net2.state_dict().items()):
+            assert torch.equal(a.to(torch.bfloat16).float(), b.float()), k
+        net8 = plora.LoRANetwork(UNet2DConditionModel(cfg), rank=8, multiplier=1.0, alpha=1.0, train_method="noxattn")
+        with pytest.raises(RuntimeError, match="shape"):
+            sio.load_slider(net8, ck)
+        netx = plora.LoRANetwork(UNet2DConditionModel(cfg), rank=4, multiplier=1.0, alpha=1.0, train_method="xattn")
+        with pytest.raises(RuntimeError, match="adaptor keys"):
+            sio.load_slider(netx, ck)
