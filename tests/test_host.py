@@ -515,3 +515,43 @@ def test_io_unet_and_slider_ingestion(tmp_path):
         netx = plora.LoRANetwork(UNet2DConditionModel(cfg), rank=4, multiplier=1.0, alpha=1.0, train_method="xattn")
         with pytest.raises(RuntimeError, match="adaptor keys"):
             sio.load_slider(netx, ck)
+
+
+def test_slice_tape_and_rank_assignment():
+    """Host pieces of the backward / sharding logic that need no GPU: batch slicing of a tape (autograd.slice_tape) and
+    the condition -> rank assignment of the sharded text-slider step."""
+    from sliders_b200.autograd import slice_tape
+
+    B = 2
+    rec = ("res", (object(), torch.arange(2 * 3 * 3 * 8).view(2, 3, 3, 8), None, torch.zeros(2, 16), torch.ones(2, 32, 2),
+                   torch.arange(2 * 9 * 4).view(18, 4), [torch.zeros(2 * 77, 6), 77, None]))
+    tape = [("scales", {1: ("a", 0.25)}), rec, ("skip", None)]
+    out = slice_tape(tape, 1, 2, B)
+    assert out[0] == tape[0] and out[2] == ("skip", None)
+    r = out[1][1]
+    assert r[0] is rec[1][0] and r[2] is None
+    assert r[1].shape == (1, 3, 3, 8) and torch.equal(r[1], rec[1][1][1:2])
+    assert r[3].shape == (1, 16) and r[4].shape == (1, 32, 2)
+    assert torch.equal(r[5], rec[1][5][9:18])            # token matrix [B * 9, C]: rows of sample 1
+    assert r[6][0].shape == (77, 6) and r[6][1] == 77
+    with pytest.raises(RuntimeError):
+        slice_tape(torch.zeros(5), 1, 2, B)               # not batch-major
+    # views, not copies
+    assert r[1].data_ptr() == rec[1][1][1:2].data_ptr()
+
+    # owner mapping of text_slider_step_xl: the grad-carrying prediction gets the last rank, the frozen ones the others
+    def owners(world):
+        o = {"target": world - 1}
+        for i, name in enumerate(("positive", "neutral", "unconditional")):
+            o[name] = i % max(world - 1, 1)
+        return o
+
+    assert owners(1) == {"target": 0, "positive": 0, "neutral": 0, "unconditional": 0}
+    assert owners(2) == {"target": 1, "positive": 0, "neutral": 0, "unconditional": 0}
+    assert owners(4) == {"target": 3, "positive": 0, "neutral": 1, "unconditional": 2}
+    assert owners(8)["target"] == 7 and set(owners(8).values()) == {0, 1, 2, 7}
+    import inspect
+
+    from sliders_b200 import trainer
+    src = inspect.getsource(trainer.text_slider_step_xl)
+    assert 'owner = {"target": world - 1}' in src and "i % max(world - 1, 1)" in src  # the mapping tested above is the shipped one
