@@ -51,7 +51,7 @@ def attn_case(B, heads, Sq, Skv, seed=0, fused_qkv=False, perf=False):
         ldq, ldk, ldv = Cc, 2 * Cc, 2 * Cc
     o = torch.full((B * Sq, Cc), float("nan"), device=dev, dtype=BF)
     scale = 1.0 / 8.0
-    args = (h, stream(), ptr(q), ldq, ptr(k), ldk, ptr(v), ldv, ptr(o), Cc, B, heads, Sq, Skv, 64, scale)
+    args = (h, stream(), ptr(q), ldq, ptr(k), ldk, ptr(v), ldv, ptr(o), Cc, B, heads, Sq, Skv, 64, scale, None)
     _cabi.check(lib.sb200_attention(*args))
     torch.cuda.synchronize()
     qf = q.float().reshape(B, Sq, heads, 64).transpose(1, 2)
