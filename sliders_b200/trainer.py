@@ -4,6 +4,7 @@
   text_slider_step      trainscripts/textsliders/train_lora.py:155-309      (SD1.x)
   image_slider_step_xl  trainscripts/imagesliders/train_lora-scale-xl.py:178-384 (a9; latents in place of VAE-encoded
                         image pairs — the VAE and the text encoders are off the denoise path)
+  image_slider_step     trainscripts/imagesliders/train_lora-scale.py:185-330  (SD1.x)
 
 Prompt embeddings are inputs (the text encoders run once, before the loop: train_lora_xl.py:100-151).  The dataflow,
 the order of the UNet calls, where `with network:` is open, what carries grad, and the DDIM bookkeeping
@@ -213,6 +214,27 @@ def image_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler
     +scale, odd ranks: low / -scale) and, when the batch divides, each parity group splits the batch; every rank
     back-propagates its share of `loss_high + loss_low` and ONE all-reduce of the flat LoRA gradient precedes the
     identical AdamW step."""
+    return _image_slider_step(True, unet, network, noise_scheduler, optimizer, lr_scheduler, prompt_pair, latents_low,
+                              latents_high, scale_to_look, max_denoising_steps, timesteps_to, device, weight_dtype, seed,
+                              reference_dead_code, group)
+
+
+def image_slider_step(unet, network, noise_scheduler, optimizer, lr_scheduler, prompt_pair: PromptEmbedsPair,
+                      latents_low: torch.Tensor, latents_high: torch.Tensor, scale_to_look: float, *,
+                      max_denoising_steps: int = 50, timesteps_to: Optional[int] = None, device=None,
+                      weight_dtype=torch.bfloat16, seed: Optional[int] = None, reference_dead_code: bool = False,
+                      group=None):
+    """SD1.x image slider, trainscripts/imagesliders/train_lora-scale.py:185-330: the same step as `image_slider_step_xl`
+    with `predict_noise` and plain [1,77,768] embeddings (`prompt_pair.{unconditional,positive,neutral}` are tensors);
+    the reference resizes the image pair to 256 px there, i.e. latents [bs,4,32,32]."""
+    return _image_slider_step(False, unet, network, noise_scheduler, optimizer, lr_scheduler, prompt_pair, latents_low,
+                              latents_high, scale_to_look, max_denoising_steps, timesteps_to, device, weight_dtype, seed,
+                              reference_dead_code, group)
+
+
+def _image_slider_step(xl: bool, unet, network, noise_scheduler, optimizer, lr_scheduler, prompt_pair, latents_low,
+                       latents_high, scale_to_look, max_denoising_steps, timesteps_to, device, weight_dtype, seed,
+                       reference_dead_code, group):
     device = device or unet.device
     criteria = torch.nn.MSELoss()
     world, rank = _world(group)
@@ -235,14 +257,30 @@ def image_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler
         noisy_low = noise_scheduler.add_noise(latents_low.to(device).float(), noise, ts).to(weight_dtype)
         noisy_high = noise_scheduler.add_noise(latents_high.to(device).float(), noise, ts).to(weight_dtype)
         noise_scheduler.set_timesteps(1000)
-        add_time_ids = train_util.get_add_time_ids(height, width, dynamic_crops=prompt_pair.dynamic_crops,
-                                                   dtype=weight_dtype).to(device, dtype=weight_dtype)
+        add_time_ids = None
+        if xl:
+            add_time_ids = train_util.get_add_time_ids(height, width, dynamic_crops=prompt_pair.dynamic_crops,
+                                                       dtype=weight_dtype).to(device, dtype=weight_dtype)
         current_timestep = noise_scheduler.timesteps[int(timesteps_to * 1000 / max_denoising_steps)]
-        if reference_dead_code:  # :258-306, results unused by the loss
-            train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy_high,
-                                        **_xl_inputs(prompt_pair, prompt_pair.positive, add_time_ids), guidance_scale=1)
-            train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy_low,
-                                        **_xl_inputs(prompt_pair, prompt_pair.neutral, add_time_ids), guidance_scale=1)
+
+        def predict(noisy, which, lo=0, hi=None):
+            """CFG-pair prediction at guidance 1 for samples [lo, hi) of the batch."""
+            n = noisy.shape[0]
+            hi = n if hi is None else hi
+            if xl:
+                inputs = _xl_inputs(prompt_pair, which, add_time_ids)
+                if (lo, hi) != (0, n):  # [uncond x n ; cond x n] -> this shard's samples of both halves
+                    inputs = {k: torch.cat([v[lo:hi], v[n + lo:n + hi]]) for k, v in inputs.items()}
+                return train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy[lo:hi], **inputs,
+                                                   guidance_scale=1)
+            emb = train_util.concat_embeddings(prompt_pair.unconditional, which, n)
+            if (lo, hi) != (0, n):
+                emb = torch.cat([emb[lo:hi], emb[n + lo:n + hi]])
+            return train_util.predict_noise(unet, noise_scheduler, current_timestep, noisy[lo:hi], emb, guidance_scale=1)
+
+        if reference_dead_code:  # train_lora-scale-xl.py:258-306 / train_lora-scale.py:252-283, unused by the loss
+            predict(noisy_high, prompt_pair.positive)
+            predict(noisy_low, prompt_pair.neutral if xl else prompt_pair.unconditional)
     bs = noisy_low.shape[0]
     groups = world // 2 if world > 1 else 1            # batch shards per sign
     if world > 1 and (bs % groups != 0 or groups == 0):
@@ -256,12 +294,8 @@ def image_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler
                 continue
             lo, hi = parallel.shard_range(bs, rank // 2, groups)
         network.set_lora_slider(scale=sign * scale_to_look)                             # :311, :343
-        inputs = _xl_inputs(prompt_pair, which, add_time_ids)
-        if (lo, hi) != (0, bs):  # [uncond x bs ; cond x bs] -> this rank's samples of both halves
-            inputs = {k: torch.cat([v[lo:hi], v[bs + lo:bs + hi]]) for k, v in inputs.items()}
         with network:
-            pred = train_util.predict_noise_xl(unet, noise_scheduler, current_timestep, noisy[lo:hi], **inputs,
-                                               guidance_scale=1).to(device, dtype=torch.float32)
+            pred = predict(noisy, which, lo, hi).to(device, dtype=torch.float32)
         loss = criteria(pred, noise[lo:hi].to(torch.float32))                           # :338, :370
         # MSE is a mean over the batch: a shard contributes (its mean) / (number of shards)
         (loss / groups if world > 1 else loss).backward()

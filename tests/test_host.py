@@ -555,3 +555,52 @@ def test_slice_tape_and_rank_assignment():
     from sliders_b200 import trainer
     src = inspect.getsource(trainer.text_slider_step_xl)
     assert 'owner = {"target": world - 1}' in src and "i % max(world - 1, 1)" in src  # the mapping tested above is the shipped one
+
+
+def test_image_slider_step_sd_host_logic(monkeypatch):
+    """`trainer.image_slider_step` (train_lora-scale.py:185-330) with a differentiable stand-in for the UNet call site:
+    both signs are applied, gradients of the two losses accumulate, the optimizer steps once."""
+    from sliders_b200 import trainer, train_util
+    from sliders_b200.scheduler import create_noise_scheduler
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.full((4, 4), 0.1))
+            self.multiplier, self.lora_scale, self.seen = 0.0, 1.0, []
+
+        def set_lora_slider(self, scale):
+            self.lora_scale = scale
+
+        def __enter__(self):
+            self.multiplier = self.lora_scale
+            self.seen.append(self.lora_scale)
+
+        def __exit__(self, *a):
+            self.multiplier = 0.0
+
+    net = Net()
+    calls = []
+
+    def predict_noise(unet, sched, t, lat, emb, guidance_scale=7.5):
+        assert emb.shape[0] == 2 * lat.shape[0] and guidance_scale == 1
+        calls.append(float(emb[lat.shape[0]:].mean()))
+        return torch.tanh(lat.float()) + net.multiplier * torch.einsum("oc,bchw->bohw", net.a, lat.float())
+
+    monkeypatch.setattr(train_util, "predict_noise", predict_noise)
+    g = torch.Generator().manual_seed(0)
+    unc, pos, neu = (torch.randn(1, 77, 8, generator=g) for _ in range(3))
+    pair = trainer.PromptEmbedsPair(torch.nn.MSELoss(), pos, pos, unc, neu, trainer.PromptSettings(batch_size=2))
+    low = torch.randn(2, 4, 8, 8, generator=g)
+    high = low + 0.1
+    opt = torch.optim.SGD(net.parameters(), lr=0.5)
+    before = net.a.detach().clone()
+    losses = trainer.image_slider_step(None, net, create_noise_scheduler("ddim"), opt, None, pair, low, high, 3.0,
+                                       timesteps_to=10, seed=1, device="cpu", weight_dtype=torch.float32)
+    assert net.seen == [3.0, -3.0] and len(calls) == 2 and len(losses) == 2
+    assert abs(calls[0] - float(pos.mean())) < 1e-6 and abs(calls[1] - float(neu.mean())) < 1e-6
+    assert not torch.equal(before, net.a.detach()) and net.multiplier == 0.0
+    calls.clear()
+    trainer.image_slider_step(None, net, create_noise_scheduler("ddim"), opt, None, pair, low, high, 3.0, timesteps_to=10,
+                              seed=1, device="cpu", weight_dtype=torch.float32, reference_dead_code=True)
+    assert len(calls) == 4
