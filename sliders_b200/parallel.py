@@ -94,3 +94,49 @@ def cfg_split_eps(eps_half: torch.Tensor, group: Optional[dist.ProcessGroup] = N
     parts = [torch.empty_like(eps_half) for _ in range(world)]
     dist.all_gather(parts, eps_half, group=group)
     return torch.cat([parts[0], parts[1]], dim=0)
+
+
+def sync_draws(values: Sequence[float], device, group: Optional[dist.ProcessGroup] = None) -> List[float]:
+    """Everything an iteration draws from the host RNG (timesteps_to, bucketed height / width, the six add_time_ids of
+    dynamic_crops, the prompt-pair index, the noise seed) travels in ONE small broadcast from group rank 0, so replicas
+    stay in lock-step whatever their per-rank seeds are (a `seed + rank` convention would otherwise hand mismatched
+    latent shapes to the next collective).  float64 carries ints up to 2**53 exactly."""
+    vals = [float(v) for v in values]
+    if group is False or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return vals
+    t = torch.tensor(vals, dtype=torch.float64, device=device)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(t, src=src, group=group)
+    return t.tolist()
+
+
+def broadcast_lora_params(network: torch.nn.Module, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Once at setup: every replica starts from group rank 0's adaptor weights (one flat broadcast per dtype)."""
+    if group is False or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    ps = list(network.parameters())
+    for dtype in {p.dtype for p in ps}:
+        same = [p for p in ps if p.dtype == dtype]
+        flat = torch.cat([p.detach().reshape(-1) for p in same])
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        with torch.no_grad():
+            for p in same:
+                p.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+
+
+def assert_replicas_equal(params: Sequence[torch.Tensor], group: Optional[dist.ProcessGroup] = None,
+                          what: str = "LoRA parameters") -> None:
+    """Cheap divergence check: (sum, sum of squares) of the flat fp64 parameter vector must agree on every rank."""
+    if group is False or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([p.detach().reshape(-1).double() for p in params])
+    sig = torch.stack([flat.sum(), (flat * flat).sum()])
+    lo, hi = sig.clone(), sig.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if not torch.equal(lo, hi):
+        raise RuntimeError(f"{what} differ between ranks (checksum min {lo.tolist()} max {hi.tolist()}): broadcast them "
+                           "once at setup (parallel.broadcast_lora_params)")

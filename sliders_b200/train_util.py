@@ -35,6 +35,41 @@ def get_initial_latents(scheduler, n_imgs: int, height: int, width: int, n_promp
     return noise * scheduler.init_noise_sigma
 
 
+def text_tokenize(tokenizer, prompts):
+    """train_util.py:59-69 (stock `transformers` CLIPTokenizer; runs once per prompt, before the loop)."""
+    return tokenizer(prompts, padding="max_length", max_length=tokenizer.model_max_length, truncation=True,
+                     return_tensors="pt").input_ids
+
+
+def text_encode(text_encoder, tokens):
+    return text_encoder(tokens.to(text_encoder.device))[0]
+
+
+def encode_prompts(tokenizer, text_encoder, prompts):
+    """SD1.x: last hidden state [n,77,768] (train_util.py:76-88)."""
+    return text_encode(text_encoder, text_tokenize(tokenizer, prompts))
+
+
+def text_encode_xl(text_encoder, tokens, num_images_per_prompt: int = 1):
+    """train_util.py:92-108: penultimate hidden state + the encoder's first output (the pooled projection for
+    text_encoder_2)."""
+    out = text_encoder(tokens.to(text_encoder.device), output_hidden_states=True)
+    pooled, hidden = out[0], out.hidden_states[-2]
+    n, seq, _ = hidden.shape
+    return hidden.repeat(1, num_images_per_prompt, 1).view(n * num_images_per_prompt, seq, -1), pooled
+
+
+def encode_prompts_xl(tokenizers, text_encoders, prompts, num_images_per_prompt: int = 1):
+    """train_util.py:111-133: hidden states of both encoders concatenated on the feature axis ([n,77,768+1280]) and
+    text_encoder_2's pooled output [n,1280]."""
+    embeds, pooled = [], None
+    for tokenizer, text_encoder in zip(tokenizers, text_encoders):
+        e, pooled = text_encode_xl(text_encoder, text_tokenize(tokenizer, prompts), num_images_per_prompt)
+        embeds.append(e)
+    n = pooled.shape[0]
+    return torch.concat(embeds, dim=-1), pooled.repeat(1, num_images_per_prompt).view(n * num_images_per_prompt, -1)
+
+
 def concat_embeddings(unconditional: torch.Tensor, conditional: torch.Tensor, n_imgs: int):
     return torch.cat([unconditional, conditional]).repeat_interleave(n_imgs, dim=0)
 

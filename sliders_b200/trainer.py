@@ -99,24 +99,33 @@ def text_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler,
     partial denoise is CFG-split: even ranks run the unconditional sample of each step, odd ranks the conditional one,
     with one 64 KiB all-gather per step (train_util._denoise_loop)."""
     device = device or unet.device
+    world, rank = _world(group)
     with torch.no_grad():
         noise_scheduler.set_timesteps(max_denoising_steps, device=device)
         optimizer.zero_grad()
+        # host-RNG draws in the reference's order (:177-203): step count, bucketed resolution, noise, crop ids
         if timesteps_to is None:
             timesteps_to = torch.randint(1, max_denoising_steps, (1,)).item()          # :177-179
-            if _world(group)[0] > 1:  # every replica must pick the same step count
-                tt = torch.tensor([timesteps_to], device=device)
-                dist.broadcast(tt, src=_global_rank(0, group), group=group)
-                timesteps_to = int(tt.item())
         height = width = prompt_pair.resolution
         if prompt_pair.dynamic_resolution:
             height, width = train_util.get_random_resolution_in_bucket(prompt_pair.resolution)
         latents = train_util.get_initial_latents(noise_scheduler, prompt_pair.batch_size, height, width, 1,
                                                  generator=generator).to(device, dtype=weight_dtype)
-        if _world(group)[0] > 1:
-            dist.broadcast(latents, src=_global_rank(0, group), group=group)  # replicas denoise the same noise
         add_time_ids = train_util.get_add_time_ids(height, width, dynamic_crops=prompt_pair.dynamic_crops,
-                                                   dtype=weight_dtype).to(device, dtype=weight_dtype)
+                                                   dtype=torch.float32)
+        if world > 1:
+            # replicas follow group rank 0's draws, whatever their own RNG state: one small broadcast carries the step
+            # count, the resolution and the six time ids, a second one the noise (its shape depends on the first)
+            vals = parallel.sync_draws([timesteps_to, height, width] + add_time_ids.flatten().tolist(), device, group)
+            timesteps_to, sh, sw = int(vals[0]), int(vals[1]), int(vals[2])
+            add_time_ids = torch.tensor([vals[3:9]], dtype=torch.float32)
+            if (sh, sw) != (height, width):
+                height, width = sh, sw
+                latents = torch.empty(prompt_pair.batch_size, train_util.UNET_IN_CHANNELS,
+                                      height // train_util.VAE_SCALE_FACTOR, width // train_util.VAE_SCALE_FACTOR,
+                                      device=device, dtype=weight_dtype)
+            dist.broadcast(latents, src=_global_rank(0, group), group=group)
+        add_time_ids = add_time_ids.to(device, dtype=weight_dtype)
         with network:                                                                   # :205-227
             denoised_latents = train_util.diffusion_xl(
                 unet, noise_scheduler, latents, **_xl_inputs(prompt_pair, prompt_pair.target, add_time_ids),
@@ -125,7 +134,6 @@ def text_slider_step_xl(unet, network, noise_scheduler, optimizer, lr_scheduler,
         noise_scheduler.set_timesteps(1000)
         current_timestep = noise_scheduler.timesteps[int(timesteps_to * 1000 / max_denoising_steps)]
         # outside `with network:` the adaptors are inert (:236-297)
-        world, rank = _world(group)
         # the grad-carrying prediction (forward + backward, ~4x a frozen one) gets a rank of its own
         owner = {"target": world - 1}
         for i, name in enumerate(("positive", "neutral", "unconditional")):
@@ -245,22 +253,21 @@ def _image_slider_step(xl: bool, unet, network, noise_scheduler, optimizer, lr_s
             timesteps_to = torch.randint(1, max_denoising_steps - 1, (1,)).item()       # :193-196
         if seed is None:
             seed = int(torch.randint(0, 2 ** 15, (1,)).item())
-        if world > 1:  # replicas must agree on the step count and on the noise
-            tt = torch.tensor([timesteps_to, seed], device=device)
-            dist.broadcast(tt, src=_global_rank(0, group), group=group)
-            timesteps_to, seed = int(tt[0].item()), int(tt[1].item())
         h, w = latents_low.shape[-2:]
         height, width = h * train_util.VAE_SCALE_FACTOR, w * train_util.VAE_SCALE_FACTOR
+        ids = train_util.get_add_time_ids(height, width, dynamic_crops=prompt_pair.dynamic_crops,
+                                          dtype=torch.float32) if xl else torch.zeros(1, 6)
+        if world > 1:  # replicas must agree on the step count, the noise seed and the (random-crop) time ids
+            vals = parallel.sync_draws([timesteps_to, seed] + ids.flatten().tolist(), device, group)
+            timesteps_to, seed = int(vals[0]), int(vals[1])
+            ids = torch.tensor([vals[2:8]], dtype=torch.float32)
         timestep = noise_scheduler.timesteps[timesteps_to]                              # get_noisy_image :224-231
         noise = torch.randn(latents_low.shape, generator=torch.Generator().manual_seed(seed)).to(device)
         ts = torch.as_tensor(timestep).reshape(1)
         noisy_low = noise_scheduler.add_noise(latents_low.to(device).float(), noise, ts).to(weight_dtype)
         noisy_high = noise_scheduler.add_noise(latents_high.to(device).float(), noise, ts).to(weight_dtype)
         noise_scheduler.set_timesteps(1000)
-        add_time_ids = None
-        if xl:
-            add_time_ids = train_util.get_add_time_ids(height, width, dynamic_crops=prompt_pair.dynamic_crops,
-                                                       dtype=weight_dtype).to(device, dtype=weight_dtype)
+        add_time_ids = ids.to(device, dtype=weight_dtype) if xl else None
         current_timestep = noise_scheduler.timesteps[int(timesteps_to * 1000 / max_denoising_steps)]
 
         def predict(noisy, which, lo=0, hi=None):
