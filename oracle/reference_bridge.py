@@ -43,8 +43,53 @@ def install_diffusers_stub() -> None:
         setattr(s, name, type(name, (), {"__init__": lambda self, *a, **k: (_ for _ in ()).throw(
             NotImplementedError("only DDIM is restated in the oracle"))}))
     d.schedulers = s
+    # imagesliders/train_util.py:7-9 additionally imports the VAE image pre-processor and `randn_tensor`
+    ip = types.ModuleType("diffusers.image_processor")
+    ip.VaeImageProcessor = VaeImageProcessor
+    ut = types.ModuleType("diffusers.utils")
+    ut.randn_tensor = randn_tensor
+    d.image_processor, d.utils = ip, ut
+    d.__path__ = []  # lets `import diffusers.x` resolve the registered sub-modules
     sys.modules["diffusers"] = d
     sys.modules["diffusers.schedulers"] = s
+    sys.modules["diffusers.image_processor"] = ip
+    sys.modules["diffusers.utils"] = ut
+
+
+class VaeImageProcessor:
+    """Restatement of diffusers 0.20.2 `VaeImageProcessor.preprocess` for PIL input with the default flags
+    (do_resize, do_normalize, no RGB conversion): round the size down to a multiple of the VAE scale factor, scale to
+    [0, 1], NHWC -> NCHW, then to [-1, 1].  Called by imagesliders/train_util.py:212-214 (`get_noisy_image`)."""
+
+    def __init__(self, vae_scale_factor: int = 8):
+        self.vae_scale_factor = vae_scale_factor
+
+    def preprocess(self, image):
+        import numpy as np
+        import torch
+
+        images = image if isinstance(image, (list, tuple)) else [image]
+        out = []
+        for im in images:
+            w, h = im.size
+            w, h = w - w % self.vae_scale_factor, h - h % self.vae_scale_factor
+            if (w, h) != im.size:
+                im = im.resize((w, h))
+            a = np.array(im).astype(np.float32) / 255.0
+            if a.ndim == 2:
+                a = a[..., None]
+            out.append(a)
+        t = torch.from_numpy(np.stack(out, axis=0).transpose(0, 3, 1, 2))
+        return 2.0 * t - 1.0
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+    """diffusers.utils.randn_tensor for a single (CPU) generator: draw on the generator's device, then move."""
+    import torch
+
+    rand_device = generator.device if generator is not None else (device or "cpu")
+    t = torch.randn(shape, generator=generator, device=rand_device, dtype=dtype, layout=layout or torch.strided)
+    return t.to(device) if device is not None else t
 
 
 def load(module: str, flavour: str = "text"):

@@ -3,24 +3,34 @@
 //   out[M, N] = epilogue( A[M, K] . W[N, K]^T  [+ scale * (A . down^T) . up^T] )
 //
 // Persistent, warp-specialised kernel, one CTA per SM, in two flavours selected on the host:
-//   kCtas = 1   128 x bn output tile per CTA  (tcgen05.mma cta_group::1, UMMA 128 x bn x 16)
-//   kCtas = 2   256 x bn tile per CTA PAIR    (cluster of 2, cta_group::2, UMMA 256 x bn x 16): each CTA stages
-//               its own 128 A rows but only HALF of the W tile, which brings the shared-memory fill rate per SM
-//               (~70 B/clk measured) below the tensor-core rate for bn = 256 — the 1-CTA kernel is fill-bound.
+//   kCtas = 1   128 x bn output tile per CTA  (tcgen05.mma cta_group::1, UMMA 128 x (bn + rt) x 16)
+//   kCtas = 2   256 x bn tile per CTA PAIR    (cluster of 2, cta_group::2, UMMA 256 x (bn + rt) x 16): each CTA stages
+//               its own 128 A rows but only HALF of the W (and LoRA-down) rows, which halves the B-operand traffic
+//               through each SM's shared memory.
 // Warp roles (320 threads):
-//   warp 0      TMA producer   — streams A / W (/ LoRA-down) tiles through an mbarrier ring of smem stages
-//   warp 1      MMA issuer     — one thread (leader CTA only) issues tcgen05.mma into a double-buffered TMEM
-//                                 accumulator; the LoRA down-projection is a second UMMA (N = rt) on the same A
-//                                 tile into spare TMEM columns
-//   warps 2..9  epilogue       — two warps per TMEM lane quarter, interleaved over 16-column chunks:
-//                                 tcgen05.ld (one row per thread), rank-r LoRA up-projection, bias / time-embedding
-//                                 row bias / GEGLU / residual; residual tiles come in by cp.async and results leave
-//                                 through a swizzled smem staging tile so that global accesses are coalesced
+//   warp 0      TMA producer   — streams A / W / LoRA-down tiles through an mbarrier ring of smem stages
+//   warp 1      MMA issuer     — (leader CTA only) tcgen05.mma into a double-buffered TMEM accumulator
+//   warps 2..9  epilogue       — two warps per TMEM lane quarter, interleaved over 32-column slabs: tcgen05.ld (one row
+//                                 per thread), rank-r LoRA up-projection, bias / time-embedding row bias / GEGLU /
+//                                 residual; residual tiles come in by cp.async and results leave through a swizzled
+//                                 smem staging tile so that global accesses are coalesced
+// Producer and issuer run as CONVERGED warps: every lane polls the mbarrier, an `elect.sync` region issues the
+// uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR).  Round 1 ran them from a `lane == 0` branch, where ptxas
+// wraps each such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~125 issue-side cycles per UMMA
+// (tools/micro/issue_bench.cu: 126 clk per UMMA at any N <= 128 against 78 converged, 48 without the handshake), which
+// is what capped narrow tiles and made the CTA-pair kernel (longer per-k-block chain) issue-bound
+// (profiles/r02_gemm_issue.md).
+//
+// The LoRA down-projection rides in the tile's own UMMA: its rows are staged right behind the W rows of the stage, so
+// the instruction's N is bn + rt and t = A . down^T lands in spare accumulator columns.  For the CTA pair each CTA
+// appends its half of the down rows to its half of the W rows; the accumulator columns are then
+//   [ W cols 0..bn/2 | t 0..rt/2 | W cols bn/2..bn | t rt/2..rt ]   (acc_col / t_col below).
 //
 // A-operand addressing modes:
 //   plain   2-D [M, K], optionally split along K over two sources (skip-connection concat, conv_shortcut)
-//   conv    4-D NHWC box per filter tap (implicit GEMM): the box start is shifted by (kh-1, kw-1) and TMA's
-//           out-of-bounds zero fill provides the padding; two sources along C give the concat
+//   conv    4-D NHWC box per filter tap (implicit GEMM): a tile is a bb x bh x bw patch of output pixels (<= 128), the
+//           box start is shifted by (kh-1, kw-1) and TMA's out-of-bounds zero fill provides the padding AND the ragged
+//           edges of patches that overhang the image, so any H x W works; two sources along C give the concat
 //   conv/2  stride-2 conv: four parity-plane descriptors (even/odd rows x even/odd columns)
 //
 // Replaces (reference): every nn.Linear / nn.Conv2d leaf that diffusers' UNet2DConditionModel executes under
@@ -50,13 +60,15 @@ struct GemmParams {
   CUtensorMap tmB;
   CUtensorMap tmL;
   int M, N, K;
-  int bn;           // accumulator tile width (UMMA N), multiple of 16
+  int bn;           // output columns of W per tile (UMMA N = bn + lora_rt), multiple of 16
   int ncols_out;    // output columns per tile (bn, or bn/2 with GEGLU)
   int Nout;         // output columns overall (N, or N/2 with GEGLU)
   int num_m_tiles, num_n_tiles;  // tiles of (128 * kCtas) x bn
+  int num_sub;      // 128-row sub-tiles along M (a CTA of a pair whose sub-tile index is >= num_sub idles through it)
   int kblocks;      // K / 64 (conv: 9 * cb_total)
   int stages;
   int stage_bytes;  // bytes of one smem stage of ONE CTA
+  int a_tx;         // bytes one A load deposits (box bytes; < 16 KB for conv patches smaller than 128 pixels)
   int b_rows;       // W rows staged per CTA per k-block (bn / kCtas)
   int l_rows;       // LoRA-down rows staged per CTA (rt / kCtas)
   int up_buf_bytes; // per-warp staging of one slab's lora_up rows: 32 * r * 4 (0 without LoRA)
@@ -65,9 +77,11 @@ struct GemmParams {
   int a_mode;       // 0 plain, 1 conv3x3 stride 1, 2 conv3x3 stride 2
   int kb_split;     // k-blocks (per tap) that come from source 0
   int cb_total;     // k-blocks per tap
-  int H, W;         // conv OUTPUT spatial dims
+  int B, H, W;      // conv OUTPUT dims
+  int bw, bh, bb;   // conv patch of one sub-tile (bw * bh * bb <= 128 pixels)
+  int tiles_w, tiles_h;
   int flags;
-  int debug;        // profiling experiments only: bit 0 skip W loads, bit 1 skip A loads (results are garbage)
+  int debug;        // profiling experiments only: bit 0 skip W loads, bit 1 skip A loads, bit 3 skip the epilogue (garbage)
   const __nv_bfloat16* bias;
   const __nv_bfloat16* rowbias;
   int rows_per_batch;
@@ -108,9 +122,34 @@ __device__ __forceinline__ void lora_apply(float* f, const float* t, uint32_t up
   }
 }
 
-// kElect: producer / MMA roles run as converged warps whose ELECTed lane issues (clean SASS) instead of a
-// `lane == 0` branch (ptxas then wraps each uniform-datapath instruction in an ELECT / BRA.U.ANY retry loop).
-template <int kCtas, bool kElect>
+// Converged-warp mbarrier wait: every lane polls (the result is warp-uniform), a protocol bug traps instead of hanging.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0) {  // keep the common path lean: the clock is read once per 256 failed polls
+      if (t0 == 0) {
+        t0 = clock64();
+      } else if (clock64() - t0 > SB200_WATCHDOG_CYCLES) {
+        if ((threadIdx.x & 31) == 0)
+          printf("sb200: mbarrier watchdog (block %d warp %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x >> 5, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+
+// First output pixel (b0, h0, w0) of conv sub-tile `st` (w fastest, then h, then batch).
+__device__ __forceinline__ void conv_origin(const GemmParams& p, int st, int& b0, int& h0, int& w0) {
+  const int tw = st % p.tiles_w;
+  const int r = st / p.tiles_w;
+  const int th = r % p.tiles_h;
+  w0 = tw * p.bw;
+  h0 = th * p.bh;
+  b0 = (r / p.tiles_h) * p.bb;
+}
+
+template <int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -170,41 +209,46 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   const int unit = blockIdx.x / kCtas;          // persistent work unit (CTA or CTA pair)
   const int num_units = gridDim.x / kCtas;
+  const int num_n_tiles = p.num_n_tiles, num_m_tiles = p.num_m_tiles, n_fast = p.n_fast;
+  const int kblocks = p.kblocks;
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.stage_bytes);
   const uint32_t a_bytes = kBM * 128;
   const uint32_t b_bytes = static_cast<uint32_t>(p.b_rows) * 128;
+  const int bn = p.bn;
+  const int rt = has_lora ? p.lora_rt : 0;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (every CTA)
-    // One lane runs the whole role.  (A converged warp with an ELECTed issuer gives cleaner SASS — no ELECT /
-    // BRA.U.ANY retry loop around every UTMALDG / UTCHMMA — but measured 12-15 % slower on B200, see
-    // profiles/r01_gemm_experiments.md, so the single-lane form stays.)
-    if (kElect || lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = unit; t < total_tiles; t += num_units) {
-        const int mt = p.n_fast ? t / p.num_n_tiles : t % p.num_m_tiles;
-        const int nt = p.n_fast ? t % p.num_n_tiles : t / p.num_m_tiles;
-        const int m0 = (mt * kCtas + static_cast<int>(cta_rank)) * kBM;
-        int b0 = 0, h0 = 0, w0 = 0;
-        if (p.a_mode != 0) {
-          const int hw = p.H * p.W;
-          b0 = m0 / hw;
-          const int rem = m0 - b0 * hw;
-          h0 = rem / p.W;
-          w0 = rem - h0 * p.W;
-        }
-        // W rows this CTA stages
-        int brow;
-        if (geglu) {
-          const int half = p.bn >> 1;
-          brow = kCtas == 2 ? (cta_rank == 0 ? nt * half : (p.N >> 1) + nt * half) : nt * half;
+    // ------------------------------------------------------------------ TMA producer (every CTA), converged warp
+    const bool skip_w = (p.debug & 1) != 0, skip_a = (p.debug & 2) != 0;
+    const int a_mode = p.a_mode, kb_split = p.kb_split, cb_total = p.cb_total;
+    const uint32_t tx = (skip_a ? 0u : static_cast<uint32_t>(p.a_tx)) + (skip_w ? 0u : b_bytes) +
+                        static_cast<uint32_t>(p.l_rows) * 128u;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = unit; t < total_tiles; t += num_units) {
+      const int mt = n_fast ? t / num_n_tiles : t % num_m_tiles;
+      const int nt = n_fast ? t % num_n_tiles : t / num_m_tiles;
+      const int st = mt * kCtas + static_cast<int>(cta_rank);  // this CTA's 128-row sub-tile
+      int m0 = st * kBM, b0 = 0, h0 = 0, w0 = 0;
+      if (a_mode != 0) {
+        if (st < p.num_sub) {
+          conv_origin(p, st, b0, h0, w0);
         } else {
-          brow = nt * p.bn + static_cast<int>(cta_rank) * p.b_rows;
+          b0 = p.B;  // phantom sub-tile of an odd pair: every box is out of bounds -> zero fill
         }
-        for (int kb = 0; kb < ((p.debug & 4) ? 0 : p.kblocks); ++kb) {
-          if (!kElect || lane == 0) mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
-          if (kElect) __syncwarp();
-          if (!kElect || elect_one()) {
+      }
+      // W rows this CTA stages
+      int brow;
+      if (geglu) {
+        const int half = bn >> 1;
+        brow = kCtas == 2 ? (cta_rank == 0 ? nt * half : (p.N >> 1) + nt * half) : nt * half;
+      } else {
+        brow = nt * bn + static_cast<int>(cta_rank) * p.b_rows;
+      }
+      int tap = 0, cb = 0;  // conv: filter tap and channel block of the current k-block
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait_warp(bar_empty + 8u * stage, phase ^ 1u);
+        if (elect_one()) {
           uint32_t full = bar_full + 8u * stage;
           if constexpr (kCtas == 2) {
             // Both CTAs' TMA bytes are counted on the LEADER's barrier; only the leader arrives (expecting the
@@ -212,31 +256,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             // stage completed (its empty barrier is released by the leader's commit after that phase), and a
             // transiently negative tx-count inside the right phase is legal.
             full = mapa_u32(full, 0);
-            if (leader)
-              mbar_expect_tx(bar_full + 8u * stage, 2u * (static_cast<uint32_t>(p.stage_bytes) - ((p.debug & 1) ? b_bytes : 0u) -
-                                                          ((p.debug & 2) ? a_bytes : 0u)));
+            if (leader) mbar_expect_tx(bar_full + 8u * stage, 2u * tx);
           } else {
-            mbar_expect_tx(full, static_cast<uint32_t>(p.stage_bytes) - ((p.debug & 1) ? b_bytes : 0u) -
-                                     ((p.debug & 2) ? a_bytes : 0u));
+            mbar_expect_tx(full, tx);
           }
-          const uint32_t sA = tiles + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const uint32_t sA = tiles + static_cast<uint32_t>(stage) * stage_bytes;
           const uint32_t sB = sA + a_bytes;
           const CUtensorMap* amap;
           int c0, c1, c2 = 0, c3 = 0;
-          if (p.a_mode == 0) {
-            const int src = kb < p.kb_split ? 0 : 1;
+          if (a_mode == 0) {
+            const int src = kb < kb_split ? 0 : 1;
             amap = &p.tmA[src];
-            c0 = (src ? kb - p.kb_split : kb) * kBK;
+            c0 = (src ? kb - kb_split : kb) * kBK;
             c1 = m0;
           } else {
-            const int tap = kb / p.cb_total;
-            const int cb = kb - tap * p.cb_total;
             const int kh = tap / 3;
             const int kw = tap - kh * 3;
-            if (p.a_mode == 1) {
-              const int src = cb < p.kb_split ? 0 : 1;
+            if (a_mode == 1) {
+              const int src = cb < kb_split ? 0 : 1;
               amap = &p.tmA[src];
-              c0 = (src ? cb - p.kb_split : cb) * kBK;
+              c0 = (src ? cb - kb_split : cb) * kBK;
               c1 = w0 + kw - 1;
               c2 = h0 + kh - 1;
             } else {
@@ -252,89 +291,79 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             c3 = b0;
           }
           if constexpr (kCtas == 2) {
-            if (!(p.debug & 2)) {
-              if (p.a_mode == 0)
+            if (!skip_a) {
+              if (a_mode == 0)
                 tma_load_2d_2cta(sA, amap, full, c0, c1);
               else
                 tma_load_4d_2cta(sA, amap, full, c0, c1, c2, c3);
             }
-            if (!(p.debug & 1)) tma_load_2d_2cta(sB, &p.tmB, full, kb * kBK, brow);
+            if (!skip_w) tma_load_2d_2cta(sB, &p.tmB, full, kb * kBK, brow);
             if (has_lora) tma_load_2d_2cta(sB + b_bytes, &p.tmL, full, kb * kBK, static_cast<int>(cta_rank) * p.l_rows);
           } else {
-            if (!(p.debug & 2)) {
-              if (p.a_mode == 0)
+            if (!skip_a) {
+              if (a_mode == 0)
                 tma_load_2d(sA, amap, full, c0, c1);
               else
                 tma_load_4d(sA, amap, full, c0, c1, c2, c3);
             }
-            if (!(p.debug & 1)) tma_load_2d(sB, &p.tmB, full, kb * kBK, brow);
-            if (geglu && !(p.debug & 1))
-              tma_load_2d(sB + static_cast<uint32_t>(p.bn >> 1) * 128, &p.tmB, full, kb * kBK,
-                          (p.N >> 1) + nt * (p.bn >> 1));
+            if (!skip_w) {
+              tma_load_2d(sB, &p.tmB, full, kb * kBK, brow);
+              if (geglu)
+                tma_load_2d(sB + static_cast<uint32_t>(bn >> 1) * 128, &p.tmB, full, kb * kBK, (p.N >> 1) + nt * (bn >> 1));
+            }
             if (has_lora) tma_load_2d(sB + b_bytes, &p.tmL, full, kb * kBK, 0);
           }
-          }
-          if (kElect) __syncwarp();
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        __syncwarp();
+        if (++cb == cb_total) {
+          cb = 0;
+          ++tap;
+        }
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if ((kElect || lane == 0) && leader) {
-      const uint32_t idesc = umma_idesc_bf16(kBM * kCtas, p.bn);
-      const uint32_t idesc_l = umma_idesc_bf16(kBM * kCtas, has_lora ? p.lora_rt : 16);
-      const uint32_t idesc_wl = umma_idesc_bf16(kBM * kCtas, p.bn + (has_lora ? p.lora_rt : 0));
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only), converged warp
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16(kBM * kCtas, bn + rt);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (int t = unit; t < total_tiles; t += num_units) {
-        if (!kElect || lane == 0) mbar_wait(bar_tempty + 8u * as, aphase ^ 1u);
-        if (kElect) __syncwarp();
+        mbar_wait_warp(bar_tempty + 8u * as, aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          if ((!kElect || lane == 0) && !(p.debug & 4)) mbar_wait(bar_full + 8u * stage, phase);
-          if (kElect) __syncwarp();
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait_warp(bar_full + 8u * stage, phase);
           tc_fence_after();
-          if (!kElect || elect_one()) {
-            const uint32_t sA = tiles + static_cast<uint32_t>(stage) * p.stage_bytes;
-            const uint32_t sB = sA + a_bytes;
-            const uint32_t sL = sB + b_bytes;
+          if (elect_one()) {
+            const uint32_t sA = tiles + static_cast<uint32_t>(stage) * stage_bytes;
             // descriptor = {hi: SBO 1024 B | version 1 | SWIZZLE_128B, lo: (address >> 4)}; +2 per 16-element k-step
-            const uint32_t a_lo = (sA & 0x3FFFF) >> 4, b_lo = (sB & 0x3FFFF) >> 4, l_lo = (sL & 0x3FFFF) >> 4;
+            const uint32_t a_lo = (sA & 0x3FFFF) >> 4, b_lo = ((sA + a_bytes) & 0x3FFFF) >> 4;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2u * k);
               const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2u * k);
               const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-              if constexpr (kCtas == 2) {
+              if constexpr (kCtas == 2)
                 umma_ss_2cta(d_tmem, adesc, bdesc, idesc, acc);
-                if (has_lora)
-                  umma_ss_2cta(d_tmem + static_cast<uint32_t>(p.bn), adesc,
-                               (static_cast<uint64_t>(kDescHi) << 32) | (l_lo + 2u * k), idesc_l, acc);
-              } else {
-                // The LoRA-down rows sit right behind the W rows in the stage and their accumulator columns right
-                // behind the tile's, so ONE UMMA of N = bn + rt covers both (each UMMA carries ~50 cycles of fixed
-                // cost on top of N/2: a separate N = 16 instruction per k-step cost +37 % main-loop time).
-                umma_ss((p.debug & 16) ? (d_tmem ^ ((k & 1) ? 256u : 0u)) : d_tmem, adesc, bdesc,
-                        has_lora ? idesc_wl : idesc, acc);  // debug 16: alternate accumulators
-              }
+              else
+                umma_ss(d_tmem, adesc, bdesc, idesc, acc);
             }
             // free the smem stage (in every CTA of the pair) once these MMAs retire
             if constexpr (kCtas == 2) {
               umma_commit_2cta(bar_empty + 8u * stage, 3);
-              if (kb == p.kblocks - 1) umma_commit_2cta(bar_tfull + 8u * as, 3);
+              if (kb == kblocks - 1) umma_commit_2cta(bar_tfull + 8u * as, 3);
             } else {
-              if (!(p.debug & 4)) umma_commit(bar_empty + 8u * stage);
-              if (kb == p.kblocks - 1) umma_commit(bar_tfull + 8u * as);
+              umma_commit(bar_empty + 8u * stage);
+              if (kb == kblocks - 1) umma_commit(bar_tfull + 8u * as);
             }
           }
-          if (kElect) __syncwarp();
+          __syncwarp();
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -347,38 +376,61 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9, every CTA)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int hsel = (warp - 2) >> 2;       // which of the two warps of this quarter (chunk parity)
+    const int hsel = (warp - 2) >> 2;       // which of the two warps of this quarter (slab parity)
     int as = 0;
     uint32_t aphase = 0;
     const float lscale =
         has_lora ? (p.lora_scale_dev ? p.lora_scale * __ldg(p.lora_scale_dev) : p.lora_scale) : 0.f;
     const bool has_resid = (p.flags & SB200_EPI_RESID) != 0;
+    const bool skip_epi = (p.debug & 8) != 0;
     const uint32_t tempty_leader = kCtas == 2 ? mapa_u32(bar_tempty, 0) : bar_tempty;
+    // accumulator column of output column c / of LoRA-down row j (see the header: the pair interleaves its halves)
+    const int half_cols = bn >> 1, lr_half = rt >> 1;
+    const bool pair_lora = kCtas == 2 && has_lora;
     // per-warp staging buffers (2 x [32 rows x 32 cols] bf16, 64 B rows, 16-byte chunks XOR-swizzled by
     // (row >> 1) & 3): residual tiles arrive here by cp.async with coalesced global reads, results leave from
     // here with coalesced global writes; in between every thread touches only its own row.
-    const uint32_t ebuf = tiles + static_cast<uint32_t>(S) * p.stage_bytes +
+    const uint32_t ebuf = tiles + static_cast<uint32_t>(S) * stage_bytes +
                           static_cast<uint32_t>(warp - 2) * (kEpiBytesPerWarp + 2 * p.up_buf_bytes);
     const uint32_t ubuf0 = ebuf + 2 * kEpiBufBytes;  // 2 x p.up_buf_bytes, same double-buffer parity as ebuf
     int bufsel = 0;
     for (int t = unit; t < total_tiles; t += num_units) {
-      const int mt = p.n_fast ? t / p.num_n_tiles : t % p.num_m_tiles;
-      const int nt = p.n_fast ? t % p.num_n_tiles : t / p.num_m_tiles;
-      const int m_q = (mt * kCtas + static_cast<int>(cta_rank)) * kBM + q * 32;  // first row of this warp
-      const int m = m_q + lane;
-      const bool row_ok = m < p.M;
+      const int mt = n_fast ? t / num_n_tiles : t % num_m_tiles;
+      const int nt = n_fast ? t % num_n_tiles : t / num_m_tiles;
+      const int st = mt * kCtas + static_cast<int>(cta_rank);
+      // output row of this thread's accumulator row (q * 32 + lane), or -1 (padding row of the tile)
+      int my_row = -1, my_batch = 0;
+      {
+        const int r = q * 32 + lane;
+        if (p.a_mode == 0) {
+          const int m = st * kBM + r;
+          if (m < p.M) my_row = m;
+          my_batch = (p.flags & SB200_EPI_ROWBIAS) ? m / p.rows_per_batch : 0;
+        } else if (st < p.num_sub) {
+          int b0, h0, w0;
+          conv_origin(p, st, b0, h0, w0);
+          const int iw = r % p.bw;
+          const int t2 = r / p.bw;
+          const int ih = t2 % p.bh;
+          const int ib = t2 / p.bh;
+          const int b = b0 + ib, h = h0 + ih, w = w0 + iw;
+          if (ib < p.bb && b < p.B && h < p.H && w < p.W) my_row = (b * p.H + h) * p.W + w;
+          my_batch = b;
+        }
+      }
+      const bool row_ok = my_row >= 0;
       const int n_base = nt * p.ncols_out;
       const int ncols_valid = min(p.ncols_out, p.Nout - n_base);
       const int nslabs = (ncols_valid + kSlab - 1) / kSlab;
-      const int my_slabs = (p.debug & 8) ? 0 : ((nslabs - hsel + 1) >> 1);  // slabs hsel, hsel+2, ... (debug 8: skip)
+      const int my_slabs = skip_epi ? 0 : ((nslabs - hsel + 1) >> 1);  // slabs hsel, hsel+2, ...
       auto prefetch_resid = [&](int col0, int sw, uint32_t buf) {
         const int cpr = sw >> 3;  // 16-byte chunks per row
         if (has_resid) {
           for (int idx = lane; idx < 32 * cpr; idx += 32) {
             const int row = idx / cpr;
             const int ch = idx - row * cpr;
-            const int mr = m_q + row;
-            if (mr < p.M)
+            const int mr = __shfl_sync(0xffffffffu, my_row, row);
+            if (mr >= 0)
               cp_async_16(buf + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4),
                           p.resid + static_cast<size_t>(mr) * p.ldr + n_base + col0 + ch * 8);
           }
@@ -397,9 +449,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       if (staged && my_slabs > 0)
         prefetch_resid(hsel * kSlab, min(kSlab, ncols_valid - hsel * kSlab), ebuf + bufsel * kEpiBufBytes);
       const __nv_bfloat16* rb =
-          (p.flags & SB200_EPI_ROWBIAS)
-              ? p.rowbias + static_cast<size_t>(row_ok ? m / p.rows_per_batch : 0) * p.Nout
-              : nullptr;
+          (p.flags & SB200_EPI_ROWBIAS) ? p.rowbias + static_cast<size_t>(row_ok ? my_batch : 0) * p.Nout : nullptr;
       mbar_wait(bar_tfull + 8u * as, aphase);
       tc_fence_after();
       const uint32_t taddr =
@@ -421,17 +471,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           const int n = n_base + c;
           uint32_t v[16];
           uint32_t g[16];
-          tmem_ld_x16(taddr + c, v);
-          if (geglu) tmem_ld_x16(taddr + (p.bn >> 1) + c, g);
+          tmem_ld_x16(taddr + c + ((pair_lora && c >= half_cols) ? lr_half : 0), v);
+          if (geglu) tmem_ld_x16(taddr + (bn >> 1) + c, g);
           if (has_lora) {
             const int grp = n / p.lora_group_n;
             if (grp != cur_group) {
               cur_group = grp;
               uint32_t tv[8];
-              tmem_ld_x8(taddr + p.bn + grp * p.lora_r, tv);
+              const int j = grp * p.lora_r;
+              tmem_ld_x8(taddr + ((pair_lora && j < lr_half) ? half_cols + j : bn + j), tv);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) tl[j] = __uint_as_float(tv[j]) * lscale;
+              for (int jj = 0; jj < 8; ++jj) tl[jj] = __uint_as_float(tv[jj]) * lscale;
             }
           }
           tmem_ld_wait();
@@ -464,7 +515,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           }
           const uint32_t a0 = buf + lane * 64 + (((2 * sub) ^ swz) << 4);
           const uint32_t a1 = buf + lane * 64 + (((2 * sub + 1) ^ swz) << 4);
-          if (has_resid) {
+          if (has_resid && row_ok) {
             const uint4 r0 = ld_shared_v4(a0), r1 = ld_shared_v4(a1);
             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -495,9 +546,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           for (int idx = lane; idx < 32 * cpr; idx += 32) {
             const int row = idx / cpr;
             const int ch = idx - row * cpr;
-            const int mr = m_q + row;
+            const int mr = __shfl_sync(0xffffffffu, my_row, row);
             const uint4 val = ld_shared_v4(buf + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
-            if (mr < p.M)
+            if (mr >= 0)
               *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(mr) * p.ldo + n_base + col0 + ch * 8) = val;
           }
         }
@@ -519,7 +570,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     }
   }
 
-  __syncwarp();  // reconverge the single-lane roles before the block / cluster barrier
+  __syncwarp();
   tc_fence_before();
   if constexpr (kCtas == 2) {
     cluster_sync_all();  // the peer's barriers / smem must outlive every multicast arrive aimed at them
@@ -543,53 +594,55 @@ struct TileChoice {
   int bn;
 };
 
-// Cost model (cycles) fitted to ncu captures (profiles/r01_*): the tensor pipe needs 2*bn clk per 64-deep k-block
-// of a 128-row (per CTA) tile; a CTA can fill shared memory at ~70 B/clk; work is dealt in waves over the
-// persistent units; each launch pays a fixed prologue and the last tile's epilogue.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
+// SB200_PAIR: 0 = never use the CTA-pair kernel, 1 = whenever the cost model prefers it (default), 2 = always.
+static int pair_policy() {
+  static const int v = env_int("SB200_PAIR", 1);
+  return v;
+}
+
+// Cost model (SM cycles per launch, fitted to the round-2 same-box measurements in profiles/r02_gemm_tiles.txt).
+// Per 64-deep k-block a CTA needs max(tensor, smem, issue):
+//   tensor  (bn + rt) / 2 cycles per UMMA, 4 UMMAs
+//   smem    every byte of the stage is written by TMA and read back by the tensor core through the same 128 B/clk
+//           port; the pair halves the W / LoRA rows per CTA
+//   issue   ~80 cycles per UMMA incl. the barrier handshake of the converged issue loop
+// and work is dealt in waves over the persistent units.
 static TileChoice pick_tile(int M, int ncols, int max_bn, int step, int num_sms, int kblocks, int lora_rt,
-                            bool allow_pair, int force_ctas) {
+                            int force_ctas, int sub_tiles) {
   double best = -1;
   TileChoice bc{1, step};
-  for (int ctas = 1; ctas <= (allow_pair ? 2 : 1); ++ctas) {
-    if (force_ctas && ctas != force_ctas) continue;
-    const int m_tiles = (M + kBM * ctas - 1) / (kBM * ctas);
+  const int pol = pair_policy();
+  for (int ctas = 1; ctas <= 2; ++ctas) {
+    if (force_ctas ? ctas != force_ctas : ((pol == 0 && ctas == 2) || (pol == 2 && ctas == 1))) continue;
+    const int m_tiles = (sub_tiles + ctas - 1) / ctas;
     const int units = num_sms / ctas;
-    for (int bn = step; bn <= max_bn; bn += step) {
-      if (ctas == 2 && (bn % 32 != 0 && step == 32)) continue;
+    const int bstep = (ctas == 2 && (lora_rt || step == 32)) ? 32 : step;
+    for (int bn = bstep; bn <= max_bn; bn += bstep) {
       const int n_tiles = (ncols + bn - 1) / bn;
       const long tiles = static_cast<long>(m_tiles) * n_tiles;
       const long waves = (tiles + units - 1) / units;
-      const double mma = 2.0 * (bn + (lora_rt ? 16 : 0));
-      const double fill = (16384.0 + (bn + lora_rt) * 128.0 / ctas) / 70.0;
-      const double perkb = mma > fill ? mma : fill;
-      const double epi = 300.0 + bn * 10.0;  // per tile, overlapped with the next tile's main loop
+      const double mma = 2.0 * (bn + lora_rt);
+      const double smem = 2.0 * (16384.0 + (bn + lora_rt) * 128.0 / ctas) / 160.0;
+      const double issue = 320.0;
+      double perkb = mma;
+      if (smem > perkb) perkb = smem;
+      if (issue > perkb) perkb = issue;
+      const double epi = 400.0 + bn * 12.0;  // per tile, overlapped with the next tile's main loop
       const double tile = kblocks * perkb > epi ? kblocks * perkb : epi;
-      const double cost = waves * tile + 4000.0 + epi;
+      const double cost = waves * tile + 4000.0 + epi + (ctas == 2 ? 1500.0 : 0.0);
       if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && bn > bc.bn)) {
         best = cost;
         bc = TileChoice{ctas, bn};
       }
     }
   }
+  (void)M;
   return bc;
-}
-
-// The CTA-pair kernel is correct (tests force it) but measured no faster than the single-CTA kernel on B200 so
-// far (profiles/README.md), so the automatic choice uses it only when SB200_ALLOW_PAIR=1.
-static bool pair_allowed() {
-  static const bool v = [] {
-    const char* e = getenv("SB200_ALLOW_PAIR");
-    return e && e[0] == '1';
-  }();
-  return v;
-}
-
-static bool elect_issue_default() {
-  static const bool v = [] {
-    const char* e = getenv("SB200_ELECT_ISSUE");
-    return e && e[0] == '1';
-  }();
-  return v;
 }
 
 static bool n_fast_default() {
@@ -602,7 +655,6 @@ static bool n_fast_default() {
 
 static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
   p.n_fast = n_fast_default() ? 1 : 0;
-  const bool elect = elect_issue_default() != ((p.debug & 32) != 0);  // debug bit 32 flips the default
   const bool has_lora = p.flags & SB200_EPI_LORA;
   p.b_rows = p.bn / ctas;
   p.l_rows = has_lora ? p.lora_rt / ctas : 0;
@@ -615,20 +667,15 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
   p.stages = stages;
   const int smem = kBarRegion + 1024 + stages * p.stage_bytes + epi_bytes;
   if (!ctx->gemm_attr_set) {
-    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     ctx->gemm_attr_set = true;
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   pdl_hint() = total <= 2 * ctx->num_sms;
   if (ctas == 1) {
     const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-    if (elect)
-      SB200_CUDA_CHECK(launch_pdl(gemm_kernel<1, true>, dim3(grid), dim3(kGemmThreads), smem, stream, p));
-    else
-      SB200_CUDA_CHECK(launch_pdl(gemm_kernel<1, false>, dim3(grid), dim3(kGemmThreads), smem, stream, p));
+    SB200_CUDA_CHECK(launch_pdl(gemm_kernel<1>, dim3(grid), dim3(kGemmThreads), smem, stream, p));
   } else {
     const int units = ctx->num_sms / 2;
     const int grid = 2 * (total < units ? total : units);
@@ -645,10 +692,7 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (elect)
-      SB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<2, true>, p));
-    else
-      SB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<2, false>, p));
+    SB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<2>, p));
   }
   SB200_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -665,11 +709,20 @@ static int check_lora(const sb200_lora* l, int N) {
 }
 
 // bn encodes an explicit choice when > 0: low 12 bits = tile width, bit 12 set = force the CTA-pair kernel,
-// bit 13 set = force the single-CTA kernel (used by the tests to cover both).
+// bit 13 set = force the single-CTA kernel (used by the tests to cover both), bits 14.. = debug bits.
 static void decode_bn(int bn_arg, int* bn, int* force_ctas, int* debug = nullptr) {
   if (debug) *debug = bn_arg > 0 ? (bn_arg >> 14) & 63 : 0;
   *force_ctas = (bn_arg > 0 && (bn_arg & 0x1000)) ? 2 : ((bn_arg > 0 && (bn_arg & 0x2000)) ? 1 : 0);
   *bn = bn_arg > 0 ? (bn_arg & 0xFFF) : 0;
+}
+
+static void fill_lora(GemmParams& p, const sb200_lora* lora) {
+  p.lora_up = static_cast<const float*>(lora->up);
+  p.lora_r = lora->r;
+  p.lora_rt = lora->rt;
+  p.lora_group_n = lora->group_n;
+  p.lora_scale = lora->scale;
+  p.lora_scale_dev = lora->scale_dev;
 }
 
 }  // namespace sb200
@@ -710,29 +763,27 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
   p.a_mode = 0;
   p.kb_split = split ? K0 / kBK : p.kblocks;
   p.cb_total = p.kblocks;
+  p.a_tx = kBM * 128;
+  p.num_sub = (M + kBM - 1) / kBM;
   int max_bn = 256;
   if (has_lora) {
     int st = check_lora(lora, N);
     if (st) return st;
     max_bn = 256 - lora->rt;
-    p.lora_up = static_cast<const float*>(lora->up);
-    p.lora_r = lora->r;
-    p.lora_rt = lora->rt;
-    p.lora_group_n = lora->group_n;
-    p.lora_scale = lora->scale;
-    p.lora_scale_dev = lora->scale_dev;
+    fill_lora(p, lora);
   }
   const int step = geglu ? 32 : 16;
   int bn, force_ctas;
   decode_bn(bn_arg, &bn, &force_ctas, &p.debug);
-  TileChoice tc = pick_tile(M, N, max_bn, step, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, pair_allowed(), force_ctas);
+  TileChoice tc = pick_tile(M, N, max_bn, step, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, force_ctas, p.num_sub);
   if (bn > 0) tc.bn = bn;
   if (force_ctas) tc.ctas = force_ctas;
-  SB200_REQUIRE(tc.bn % step == 0 && tc.bn >= step && tc.bn <= max_bn, "gemm: bn=%d invalid (step %d, max %d)",
-                tc.bn, step, max_bn);
+  const int need = (tc.ctas == 2 && (has_lora || geglu)) ? 32 : step;
+  SB200_REQUIRE(tc.bn % need == 0 && tc.bn >= need && tc.bn <= max_bn, "gemm: bn=%d invalid (step %d, max %d)",
+                tc.bn, need, max_bn);
   p.bn = tc.bn;
   p.ncols_out = geglu ? tc.bn / 2 : tc.bn;
-  p.num_m_tiles = (M + kBM * tc.ctas - 1) / (kBM * tc.ctas);
+  p.num_m_tiles = (p.num_sub + tc.ctas - 1) / tc.ctas;
   p.num_n_tiles = (p.Nout + p.ncols_out - 1) / p.ncols_out;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.rowbias = static_cast<const __nv_bfloat16*>(rowbias);
@@ -771,6 +822,29 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
   return launch_gemm(ctx, static_cast<cudaStream_t>(stream), p, tc.ctas);
 }
 
+// Patch of output pixels one 128-row sub-tile covers: bw x bh x bb with bw * bh * bb <= 128, chosen to minimise the
+// number of sub-tiles (ties: the widest patch row, i.e. the longest contiguous TMA runs).  bb > 1 only for whole images.
+static void pick_patch(int B, int H, int W, int* bw_o, int* bh_o, int* bb_o) {
+  long best = -1;
+  int sel_w = 1, sel_h = 1, sel_b = 1;
+  for (int bw = (W < 128 ? W : 128); bw >= 1; --bw) {
+    int bh = 128 / bw;
+    if (bh > H) bh = H;
+    int bb = 1;
+    if (bw == W && bh == H) {
+      bb = 128 / (bw * bh);
+      if (bb > B) bb = B;
+      if (bb < 1) bb = 1;
+    }
+    const long tiles = static_cast<long>((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((B + bb - 1) / bb);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      sel_w = bw, sel_h = bh, sel_b = bb;
+    }
+  }
+  *bw_o = sel_w, *bh_o = sel_h, *bb_o = sel_b;
+}
+
 extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx0, const void* x1,
                              int ldx1, int C0, int C1, const void* w, void* out, int ldo, int B, int Hin,
                              int Win, int Cout, int stride, int flags, const void* bias,
@@ -779,7 +853,8 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "conv3x3: NULL handle");
   SB200_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride %d", stride);
-  SB200_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Hin % stride == 0 && Win % stride == 0, "conv3x3: dims");
+  SB200_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Hin % stride == 0 && Win % stride == 0,
+                "conv3x3: %dx%d input with stride %d (stride 2 needs even dims)", Hin, Win, stride);
   if (!x1) C1 = 0;
   SB200_REQUIRE(C0 > 0 && C0 % 64 == 0 && C1 % 64 == 0, "conv3x3: C0=%d C1=%d must be multiples of 64", C0,
                 C1);
@@ -793,23 +868,8 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
   SB200_REQUIRE(!(flags & SB200_EPI_ROWBIAS) || rowbias, "conv3x3: ROWBIAS without rowbias");
   SB200_REQUIRE(!(flags & SB200_EPI_RESID) || (resid && ldr % 8 == 0), "conv3x3: RESID args");
   const int H = Hin / stride, W = Win / stride;
-  // 128 output pixels per CTA tile = bb images x bh rows x bw columns, contiguous in NHWC order
   int bw, bh, bb;
-  if (W >= 128) {
-    SB200_REQUIRE(W % 128 == 0, "conv3x3: W=%d must be a multiple of 128 or divide 128", W);
-    bw = 128, bh = 1, bb = 1;
-  } else {
-    SB200_REQUIRE(128 % W == 0, "conv3x3: W=%d must divide 128", W);
-    bw = W;
-    const int rows = 128 / W;
-    if (rows <= H) {
-      SB200_REQUIRE(H % rows == 0, "conv3x3: H=%d must be a multiple of %d", H, rows);
-      bh = rows, bb = 1;
-    } else {
-      SB200_REQUIRE(rows % H == 0, "conv3x3: H=%d must divide %d", H, rows);
-      bh = H, bb = rows / H;
-    }
-  }
+  pick_patch(B, H, W, &bw, &bh, &bb);
   const int Cin = C0 + C1;
   const int M = B * H * W;
 
@@ -824,29 +884,33 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
   p.kblocks = 9 * p.cb_total;
   p.a_mode = stride == 1 ? 1 : 2;
   p.kb_split = C0 / kBK;
+  p.B = B;
   p.H = H;
   p.W = W;
+  p.bw = bw;
+  p.bh = bh;
+  p.bb = bb;
+  p.tiles_w = (W + bw - 1) / bw;
+  p.tiles_h = (H + bh - 1) / bh;
+  p.num_sub = p.tiles_w * p.tiles_h * ((B + bb - 1) / bb);
+  p.a_tx = bw * bh * bb * 128;
   int max_bn = 256;
   if (has_lora) {
     int st = check_lora(lora, Cout);
     if (st) return st;
     max_bn = 256 - lora->rt;
-    p.lora_up = static_cast<const float*>(lora->up);
-    p.lora_r = lora->r;
-    p.lora_rt = lora->rt;
-    p.lora_group_n = lora->group_n;
-    p.lora_scale = lora->scale;
-    p.lora_scale_dev = lora->scale_dev;
+    fill_lora(p, lora);
   }
   int bn, force_ctas;
-  decode_bn(bn_arg, &bn, &force_ctas);
-  TileChoice tc = pick_tile(M, Cout, max_bn, 16, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, pair_allowed(), force_ctas);
+  decode_bn(bn_arg, &bn, &force_ctas, &p.debug);
+  TileChoice tc = pick_tile(M, Cout, max_bn, 16, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, force_ctas, p.num_sub);
   if (bn > 0) tc.bn = bn;
   if (force_ctas) tc.ctas = force_ctas;
-  SB200_REQUIRE(tc.bn % 16 == 0 && tc.bn >= 16 && tc.bn <= max_bn, "conv3x3: bn=%d invalid", tc.bn);
+  const int need = (tc.ctas == 2 && has_lora) ? 32 : 16;
+  SB200_REQUIRE(tc.bn % need == 0 && tc.bn >= need && tc.bn <= max_bn, "conv3x3: bn=%d invalid (step %d)", tc.bn, need);
   p.bn = tc.bn;
   p.ncols_out = tc.bn;
-  p.num_m_tiles = (M + kBM * tc.ctas - 1) / (kBM * tc.ctas);
+  p.num_m_tiles = (p.num_sub + tc.ctas - 1) / tc.ctas;
   p.num_n_tiles = (Cout + tc.bn - 1) / tc.bn;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.rowbias = static_cast<const __nv_bfloat16*>(rowbias);

@@ -14,14 +14,15 @@ from typing import Callable, Optional
 
 import torch
 
-from . import ops
+from . import train_util
 
 
 @torch.no_grad()
 def denoise_loop(unet, network, scheduler, latents: torch.Tensor, prompt_embeds: torch.Tensor,
                  add_text_embeds: Optional[torch.Tensor] = None, add_time_ids: Optional[torch.Tensor] = None, *,
                  num_inference_steps: int = 50, guidance_scale: float = 5.0, scale: float = 0.0,
-                 start_noise: int = 750, callback: Optional[Callable] = None) -> torch.Tensor:
+                 start_noise: int = 750, callback: Optional[Callable] = None,
+                 generator: Optional[torch.Generator] = None) -> torch.Tensor:
     """latents: [N,4,h,w] already multiplied by `scheduler.init_noise_sigma`; prompt_embeds: [2N,77,D] as
     (negative ; positive) like `encode_prompt` + `torch.cat` produce (generate_images_xl.py:251-307);
     add_text_embeds [2N,1280] / add_time_ids [2N,6] for SDXL, None for SD1.x.  Returns the final latents."""
@@ -38,18 +39,8 @@ def denoise_loop(unet, network, scheduler, latents: torch.Tensor, prompt_embeds:
         with network:
             kwargs = {"added_cond_kwargs": added} if added is not None else {}
             noise_pred = unet(x, t, encoder_hidden_states=prompt_embeds, return_dict=False, **kwargs)[0]
-        # guidance (:349-351) and scheduler.step (:358) in one kernel when the scheduler is our DDIM
-        if hasattr(scheduler, "_alphas_for"):
-            a_t, a_prev = scheduler._alphas_for(t)
-            _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), a_t, a_prev,
-                                      out_dtype=latents.dtype)
-        elif getattr(scheduler, "affine_step", False):  # sliders_b200 EulerDiscreteScheduler: x' = cx x + ce eps
-            cx, ce = scheduler._step_coeffs(t)
-            _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), cx, ce,
-                                      out_dtype=latents.dtype, affine=True)
-        else:
-            guided, _ = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, out_dtype=noise_pred.dtype)
-            latents = scheduler.step(guided, t, latents, return_dict=False)[0]
+        # guidance (:349-351) and scheduler.step (:358): one kernel for DDIM / Euler, + noise for the ancestral samplers
+        latents = train_util.guided_step(scheduler, noise_pred, t, latents, guidance_scale, generator)
         if callback is not None:
             callback(i, t, latents)
     return latents

@@ -25,6 +25,9 @@ class DDIMSchedulerOutput(SimpleNamespace):
 
 class DDIMScheduler:
     order = 1
+    # how the denoise loops fuse guidance + step into `cfg_ddim_kernel`: "ddim" (alpha-bar pair), "affine"
+    # (x' = cx x + ce eps), "affine+noise" (+ std * z), "generic" (scheduler.step on the guided eps)
+    step_kind = "ddim"
 
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
                  beta_schedule: str = "scaled_linear", clip_sample: bool = False, set_alpha_to_one: bool = True,
@@ -113,7 +116,7 @@ class EulerDiscreteScheduler:
     host; on CUDA tensors `step` is one `cfg_ddim_kernel` launch in its affine mode (x_next = x + (sigma' - sigma) eps),
     and `generate.denoise_loop` fuses the guidance into the same launch through `_step_coeffs`."""
     order = 1
-    affine_step = True  # x_next = cx x + ce eps with host-side (cx, ce): eligible for the fused guidance + step kernel
+    step_kind = "affine"  # x_next = cx x + ce eps with host-side (cx, ce): eligible for the fused guidance + step kernel
 
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
                  beta_schedule: str = "scaled_linear", prediction_type: str = "epsilon",
@@ -205,7 +208,7 @@ class LMSDiscreteScheduler(EulerDiscreteScheduler):
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
                  beta_schedule: str = "scaled_linear", prediction_type: str = "epsilon",
                  timestep_spacing: str = "linspace", steps_offset: int = 0):
-        # (the class attribute `affine_step = False` below keeps generate.denoise_loop on its generic scheduler.step branch)
+        # (the class attribute `step_kind = "generic"` below keeps the denoise loops on their scheduler.step branch)
         super().__init__(num_train_timesteps, beta_start, beta_end, beta_schedule, prediction_type, "linear", False,
                          timestep_spacing, steps_offset)
         self.derivatives = []
@@ -229,7 +232,7 @@ class LMSDiscreteScheduler(EulerDiscreteScheduler):
 
         return integrate.quad(lms_derivative, sig[t], sig[t + 1], epsrel=1e-4)[0]
 
-    affine_step = False  # multistep: not an affine function of (x, eps) alone
+    step_kind = "generic"  # multistep: not an affine function of (x, eps) alone
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, order: int = 4,
              return_dict: bool = True, **unused):
@@ -249,17 +252,109 @@ class LMSDiscreteScheduler(EulerDiscreteScheduler):
         return DDIMSchedulerOutput(prev_sample=prev)
 
 
+def _noise_like(model_output: torch.Tensor, generator: Optional[torch.Generator]) -> torch.Tensor:
+    """diffusers' `randn_tensor(model_output.shape, generator=…, device=…, dtype=…)`: drawn on the generator's device
+    (or the tensor's, from the global RNG), then moved."""
+    dev = generator.device if generator is not None else model_output.device
+    return torch.randn(model_output.shape, generator=generator, device=dev, dtype=model_output.dtype).to(model_output.device)
+
+
+class DDPMScheduler(DDIMScheduler):
+    """diffusers' `DDPMScheduler` as model_util.py:247-256 builds it (scaled_linear betas, 1000 train steps,
+    clip_sample=False, epsilon prediction; library defaults: variance_type "fixed_small", "leading" spacing) — the
+    ancestral sampler behind `train.noise_scheduler: "ddpm"`.  Same grid, `add_noise`, `init_noise_sigma` and
+    `scale_model_input` as DDIM; the step is the posterior mean, affine in (x, eps) with host-side coefficients (one
+    `cfg_ddim_kernel` launch in its affine mode), plus sqrt(posterior variance) * z for t > 0."""
+    step_kind = "affine+noise"
+
+    def _abar(self, timestep):
+        t = int(timestep)
+        prev = t - self.config.num_train_timesteps // self.num_inference_steps
+        return t, self._acp[t], (self._acp[prev] if prev >= 0 else 1.0)
+
+    def _step_coeffs(self, timestep) -> tuple:
+        """(cx, ce) of the posterior mean  cx x + ce eps."""
+        _, a_t, a_prev = self._abar(timestep)
+        b_t, b_prev = 1.0 - a_t, 1.0 - a_prev
+        cur_a = a_t / a_prev
+        c0 = (a_prev ** 0.5) * (1.0 - cur_a) / b_t          # weight of x0 = (x - sqrt(b_t) eps) / sqrt(a_t)
+        return c0 / a_t ** 0.5 + cur_a ** 0.5 * b_prev / b_t, -c0 * (b_t / a_t) ** 0.5
+
+    def _noise_std(self, timestep) -> float:
+        t, a_t, a_prev = self._abar(timestep)
+        if t <= 0:
+            return 0.0
+        return max((1.0 - a_prev) / (1.0 - a_t) * (1.0 - a_t / a_prev), 1e-20) ** 0.5
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, generator: Optional[torch.Generator] = None,
+             return_dict: bool = True, **unused):
+        if self.num_inference_steps is None:
+            raise ValueError("call set_timesteps first")
+        cx, ce = self._step_coeffs(timestep)
+        if model_output.is_cuda:
+            out_dtype = sample.dtype if sample.dtype in (torch.float32, torch.bfloat16) else torch.float32
+            _, prev = ops.cfg_ddim(model_output.contiguous(), 0.0, sample.contiguous(), cx, ce, out_dtype=out_dtype,
+                                   single=True, affine=True)
+            prev = prev.to(sample.dtype)
+        else:  # host tensors (scheduler unit tests); not a model path
+            prev = cx * sample + ce * model_output
+        std = self._noise_std(timestep)
+        if std > 0.0:
+            prev = prev + std * _noise_like(model_output, generator).to(prev.dtype)
+        if not return_dict:
+            return (prev,)
+        return DDIMSchedulerOutput(prev_sample=prev)
+
+
+class EulerAncestralDiscreteScheduler(EulerDiscreteScheduler):
+    """diffusers' `EulerAncestralDiscreteScheduler` as model_util.py:266-274 builds it (scaled_linear betas, "linspace"
+    spacing): Euler step to sigma_down plus sigma_up * z.  The deterministic part is the affine mode of `cfg_ddim_kernel`."""
+    step_kind = "affine+noise"
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 beta_schedule: str = "scaled_linear", prediction_type: str = "epsilon",
+                 timestep_spacing: str = "linspace", steps_offset: int = 0):
+        super().__init__(num_train_timesteps, beta_start, beta_end, beta_schedule, prediction_type, "linear", False,
+                         timestep_spacing, steps_offset)
+
+    def _sigmas_at(self, timestep):
+        i = self._index(timestep)
+        s_from, s_to = self._sigmas_host[i], self._sigmas_host[i + 1]
+        up = (s_to * s_to * (s_from * s_from - s_to * s_to) / (s_from * s_from)) ** 0.5
+        return s_from, (s_to * s_to - up * up) ** 0.5, up
+
+    def _step_coeffs(self, timestep) -> tuple:
+        s_from, s_down, _ = self._sigmas_at(timestep)
+        return 1.0, s_down - s_from
+
+    def _noise_std(self, timestep) -> float:
+        return self._sigmas_at(timestep)[2]
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, generator: Optional[torch.Generator] = None,
+             return_dict: bool = True, **unused):
+        out = super().step(model_output, timestep, sample, return_dict=False)[0]
+        std = self._noise_std(timestep)
+        if std > 0.0:
+            out = out + std * _noise_like(model_output, generator).to(out.dtype)
+        if not return_dict:
+            return (out,)
+        return DDIMSchedulerOutput(prev_sample=out)
+
+
 def create_noise_scheduler(scheduler_name: str = "ddim", prediction_type: str = "epsilon"):
-    """model_util.create_noise_scheduler (model_util.py:230-278): the DDIM branch (the shipped configs' choice) plus
-    "euler" for the eval loop (the reference's factory itself offers ddim / ddpm / lms / euler_a)."""
+    """model_util.create_noise_scheduler (model_util.py:230-278): "ddim", "ddpm", "lms", "euler_a" as the reference's
+    factory builds them, plus "euler" (EulerDiscrete, what the SDXL eval pipeline ships with)."""
     name = scheduler_name.lower().replace(" ", "_")
+    common = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+                  prediction_type=prediction_type)
+    if name == "ddim":
+        return DDIMScheduler(clip_sample=False, **common)
+    if name == "ddpm":
+        return DDPMScheduler(clip_sample=False, **common)
+    if name == "lms":
+        return LMSDiscreteScheduler(**common)
+    if name == "euler_a":
+        return EulerAncestralDiscreteScheduler(**common)
     if name == "euler":
-        return EulerDiscreteScheduler(prediction_type=prediction_type)
-    if name == "lms":  # model_util.py:255-262
-        return LMSDiscreteScheduler(prediction_type=prediction_type)
-    if name != "ddim":
-        raise NotImplementedError(f"scheduler {scheduler_name}: sliders_b200 restates DDIM (the shipped configs' "
-                                  "choice, data/config-xl.yaml), EulerDiscrete and LMSDiscrete; DDPM / Euler-a are "
-                                  "stochastic samplers off the measured path (SURVEY.md §8f rank 3)")
-    return DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
-                         num_train_timesteps=1000, clip_sample=False, prediction_type=prediction_type)
+        return EulerDiscreteScheduler(**common)
+    raise ValueError(f"Unknown scheduler name: {name}")

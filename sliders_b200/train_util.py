@@ -142,11 +142,36 @@ def _denoise_loop(unet, scheduler, latents, text_embeddings, added, guidance_sca
             noise_pred = parallel.cfg_split_eps(half, cfg_split_group)
         else:
             noise_pred = _unet_pair(unet, x, timestep, text_embeddings, added)
-        a_t, a_prev = scheduler._alphas_for(timestep)
-        # fused: eps = u + g (c - u);  x_{t-1} = DDIM(eps, x_t)
-        _, latents = ops.cfg_ddim(noise_pred.contiguous(), guidance_scale, latents.contiguous(), a_t, a_prev,
-                                  out_dtype=latents.dtype)
+        latents = guided_step(scheduler, noise_pred, timestep, latents, guidance_scale)
     return latents
+
+
+def guided_step(scheduler, noise_pred: torch.Tensor, timestep, latents: torch.Tensor, guidance_scale: float,
+                generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """eps = u + g (c - u) followed by `scheduler.step(eps, t, x).prev_sample` (train_util.py:165-171 + :193 /
+    generate_images_xl.py:349-358).  For the schedulers whose step is affine in (x, eps) with host-side coefficients the
+    two are ONE `cfg_ddim_kernel` launch; the ancestral ones add their noise term on top; the rest (LMS) take the
+    guided eps through their own `step`."""
+    kind = getattr(scheduler, "step_kind", "generic")
+    noise_pred = noise_pred.contiguous()
+    if kind == "ddim":
+        a_t, a_prev = scheduler._alphas_for(timestep)
+        return ops.cfg_ddim(noise_pred, guidance_scale, latents.contiguous(), a_t, a_prev, out_dtype=latents.dtype)[1]
+    if kind in ("affine", "affine+noise"):
+        cx, ce = scheduler._step_coeffs(timestep)
+        out = ops.cfg_ddim(noise_pred, guidance_scale, latents.contiguous(), cx, ce, out_dtype=latents.dtype,
+                           affine=True)[1]
+        if kind == "affine+noise":
+            std = scheduler._noise_std(timestep)
+            if std > 0.0:
+                n = noise_pred.shape[0] // 2
+                dev = generator.device if generator is not None else out.device
+                z = torch.randn((n,) + tuple(noise_pred.shape[1:]), generator=generator, device=dev,
+                                dtype=noise_pred.dtype).to(out.device)
+                out = out + std * z.to(out.dtype)
+        return out
+    guided, _ = ops.cfg_ddim(noise_pred, guidance_scale, out_dtype=noise_pred.dtype)
+    return scheduler.step(guided, timestep, latents, return_dict=False)[0]
 
 
 @torch.no_grad()

@@ -250,7 +250,8 @@ def _image_slider_step(xl: bool, unet, network, noise_scheduler, optimizer, lr_s
         noise_scheduler.set_timesteps(max_denoising_steps, device=device)
         optimizer.zero_grad()
         if timesteps_to is None:
-            timesteps_to = torch.randint(1, max_denoising_steps - 1, (1,)).item()       # :193-196
+            # train_lora-scale-xl.py:191-193 draws from [1, max); the SD1.x script from [1, max - 1) (:186-189)
+            timesteps_to = torch.randint(1, max_denoising_steps if xl else max_denoising_steps - 1, (1,)).item()
         if seed is None:
             seed = int(torch.randint(0, 2 ** 15, (1,)).item())
         h, w = latents_low.shape[-2:]
@@ -263,6 +264,7 @@ def _image_slider_step(xl: bool, unet, network, noise_scheduler, optimizer, lr_s
             ids = torch.tensor([vals[2:8]], dtype=torch.float32)
         timestep = noise_scheduler.timesteps[timesteps_to]                              # get_noisy_image :224-231
         noise = torch.randn(latents_low.shape, generator=torch.Generator().manual_seed(seed)).to(device)
+        noise_w = noise.to(weight_dtype)   # the loss target is the noise as stored in weight_dtype (:235, :251)
         ts = torch.as_tensor(timestep).reshape(1)
         noisy_low = noise_scheduler.add_noise(latents_low.to(device).float(), noise, ts).to(weight_dtype)
         noisy_high = noise_scheduler.add_noise(latents_high.to(device).float(), noise, ts).to(weight_dtype)
@@ -303,7 +305,7 @@ def _image_slider_step(xl: bool, unet, network, noise_scheduler, optimizer, lr_s
         network.set_lora_slider(scale=sign * scale_to_look)                             # :311, :343
         with network:
             pred = predict(noisy, which, lo, hi).to(device, dtype=torch.float32)
-        loss = criteria(pred, noise[lo:hi].to(torch.float32))                           # :338, :370
+        loss = criteria(pred, noise_w[lo:hi].to(torch.float32))                         # :338, :370
         # MSE is a mean over the batch: a shard contributes (its mean) / (number of shards)
         (loss / groups if world > 1 else loss).backward()
         losses[i] = loss.detach() / (groups if world > 1 else 1)

@@ -76,8 +76,10 @@ def test_model_sources():
     with pytest.raises(FileNotFoundError, match="never downloads"):
         model_util._resolve("stabilityai/definitely-not-cached")
     assert model_util._resolve("synthetic:7") == ("synthetic", "synthetic:7")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         model_util.create_noise_scheduler("plms")
+    for name in model_util.AVAILABLE_SCHEDULERS:        # every name the reference's factory accepts
+        assert model_util.create_noise_scheduler(name) is not None
 
 
 @needs_ref

@@ -55,6 +55,9 @@ def make_lora(K, N, r, group_n, dev, seed, conv_cin=None):
     (1024, 1920, 640, "L", 0, (4, 640, 1.0)),   # fused to_q|to_k|to_v, three adaptors
     (512, 640, 640, "bRL", 0, (8, 640, -2.0)),  # rank 8, negative slider
     (4096, 1280, 1280, "btR", 0, None),         # row bias (time embedding) + residual
+    (300, 3840, 1280, "L", 0, (4, 1280, 1.0)),  # fused QKV at SDXL width: the pair interleaves W / LoRA halves
+    (640, 2560, 640, "bRL", 0, (8, 1280, 0.5)), # rank 8, two adaptors, rt = 16: one adaptor per pair half
+    (129, 320, 320, "bRL", 0, (4, 320, 1.0)),   # odd number of 128-row sub-tiles: phantom half of the last pair
 ])
 def test_gemm(dev, force, M, N, K, flags, split, lora):
     from sliders_b200 import ops
@@ -105,6 +108,14 @@ def test_gemm(dev, force, M, N, K, flags, split, lora):
     (2, 32, 32, 640, 0, 640, 1, "bL", (4, 0.5)),   # LoRA conv: down 3x3 folded in, up 1x1 in the epilogue
     (3, 8, 8, 128, 0, 128, 1, "b", None),          # 8x8 level: tiles span images, ragged M
     (1, 16, 16, 128, 64, 64, 1, "b", None),
+    # patches that overhang the image (dynamic_resolution buckets, non-square eval sizes: ADVICE r1 #1)
+    (1, 72, 72, 64, 0, 64, 1, "bR", None),         # W = 72: one 72-pixel row per 128-row tile
+    (2, 36, 88, 128, 0, 128, 1, "bt", (4, 0.5)),   # 36 x 88, LoRA + time-embedding bias
+    (1, 18, 18, 128, 64, 64, 1, "b", None),        # 18 x 18 with a skip concat (7 rows of 18 per tile)
+    (3, 9, 11, 64, 0, 64, 1, "bR", None),          # 99-pixel images: one (ragged) image per tile
+    (2, 72, 104, 64, 0, 64, 2, "b", None),         # stride 2 to 36 x 52
+    (1, 96, 160, 64, 0, 64, 1, "b", None),         # W > 128 and not a multiple of it
+    (5, 4, 4, 64, 0, 64, 1, "bt", None),           # 8 images per tile, 5 in the batch
 ])
 def test_conv3x3(dev, force, B, H, W, C0, C1, Cout, stride, flags, lora):
     from sliders_b200 import ops

@@ -465,7 +465,7 @@ def test_lms_scheduler_matches_oracle_restatement():
 
     a = psched.create_noise_scheduler("lms")
     b = olms.LMSDiscreteScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
-    assert isinstance(a, psched.LMSDiscreteScheduler) and not a.affine_step
+    assert isinstance(a, psched.LMSDiscreteScheduler) and a.step_kind == "generic"
     a.set_timesteps(12)
     b.set_timesteps(12)
     assert torch.equal(a.timesteps, b.timesteps) and torch.allclose(a.sigmas, b.sigmas)
@@ -604,3 +604,38 @@ def test_image_slider_step_sd_host_logic(monkeypatch):
     trainer.image_slider_step(None, net, create_noise_scheduler("ddim"), opt, None, pair, low, high, 3.0, timesteps_to=10,
                               seed=1, device="cpu", weight_dtype=torch.float32, reference_dead_code=True)
     assert len(calls) == 4
+
+
+def test_stochastic_schedulers_match_oracle_restatement():
+    """`train.noise_scheduler: "ddpm" | "euler_a"` (model_util.py:247-278): sliders_b200.scheduler against
+    oracle/stochastic.py over whole trajectories with the same generator stream."""
+    from oracle import stochastic as ost
+    from sliders_b200 import scheduler as psched
+
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    pairs = ((psched.create_noise_scheduler("ddpm"), ost.DDPMScheduler(clip_sample=False, **kw)),
+             (psched.create_noise_scheduler("euler_a"), ost.EulerAncestralDiscreteScheduler(**kw)))
+    assert isinstance(pairs[0][0], psched.DDPMScheduler) and isinstance(pairs[1][0], psched.EulerAncestralDiscreteScheduler)
+    for a, b in pairs:
+        assert a.step_kind == "affine+noise"
+        assert abs(float(a.init_noise_sigma) - float(b.init_noise_sigma)) < 1e-4
+        for n in (50, 11):
+            a.set_timesteps(n)
+            b.set_timesteps(n)
+            assert torch.equal(a.timesteps.double(), b.timesteps.double())
+            g = torch.Generator().manual_seed(n)
+            x0 = torch.randn(2, 4, 8, 8, generator=g) * float(a.init_noise_sigma)
+            xa = xb = x0
+            ga, gb = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+            for t in a.timesteps_host:
+                e = torch.randn(2, 4, 8, 8, generator=g)
+                assert torch.allclose(a.scale_model_input(xa, t), b.scale_model_input(xb, t), atol=1e-5)
+                xa = a.step(e, t, xa, generator=ga).prev_sample
+                xb = b.step(e, t, xb, generator=gb).prev_sample
+                assert torch.allclose(xa, xb, rtol=1e-4, atol=1e-4), (type(a).__name__, n, t)
+    # the noise term is really there (and absent at the last DDPM step, t = 0)
+    d = pairs[0][0]
+    d.set_timesteps(1000)
+    assert d._noise_std(0) == 0.0 and d._noise_std(500) > 0.0
+    with pytest.raises(ValueError):
+        psched.create_noise_scheduler("plms")

@@ -316,3 +316,44 @@ def test_lms_discrete_properties():
         if i >= 3:
             assert abs(float(x_next) - F(float(l.sigmas[i + 1]))) < 2e-3, i
         x = torch.tensor([F(float(l.sigmas[i + 1]))], dtype=torch.float64)  # restart from the exact value
+
+
+def test_stochastic_sampler_identities():
+    """oracle/stochastic.py (DDPM / Euler-ancestral restatements) against closed forms that do not depend on the
+    restatement: the DDPM posterior q(x_{t-1} | x_t, x_0) and the ancestral variance split."""
+    from oracle import stochastic as ost
+
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    d = ost.DDPMScheduler(clip_sample=False, **kw)
+    d.set_timesteps(1000)
+    acp = d.alphas_cumprod.double()
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn(1, 4, 8, 8, generator=g).double()
+    eps = torch.randn(1, 4, 8, 8, generator=g).double()
+    for t in (999, 500, 37, 1):
+        xt = d.add_noise(x0, eps, torch.tensor([t]))
+        # with the TRUE eps the predicted x0 is exact, so the step's mean is the posterior mean of Ho et al. eq. 7
+        zeros = torch.Generator().manual_seed(1)
+        out = d.step(eps, t, xt, generator=zeros)
+        assert torch.allclose(out.pred_original_sample, x0, atol=1e-5)
+        beta_t = 1 - acp[t] / acp[t - 1]
+        mean = (acp[t - 1].sqrt() * beta_t / (1 - acp[t])) * x0 + ((acp[t] / acp[t - 1]).sqrt() * (1 - acp[t - 1]) / (1 - acp[t])) * xt
+        var = (1 - acp[t - 1]) / (1 - acp[t]) * beta_t
+        z = torch.randn(xt.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+        assert torch.allclose(out.prev_sample, mean + var.sqrt() * z, atol=1e-5)
+    # t = 0: no noise, the step returns x0 itself
+    xt = d.add_noise(x0, eps, torch.tensor([0]))
+    assert torch.allclose(d.step(eps, 0, xt).prev_sample, x0, atol=1e-5)
+
+    e = ost.EulerAncestralDiscreteScheduler(**kw)
+    e.set_timesteps(30)
+    s = e.sigmas.double()
+    assert abs(float(e.init_noise_sigma) - 14.6146) < 1e-3 and float(s[-1]) == 0.0
+    for i in range(30):
+        up2 = s[i + 1] ** 2 * (s[i] ** 2 - s[i + 1] ** 2) / s[i] ** 2
+        down2 = s[i + 1] ** 2 - up2
+        assert up2 >= 0 and down2 >= -1e-12 and abs(float(up2 + down2 - s[i + 1] ** 2)) < 1e-9
+    # noise-free part == an Euler step to sigma_down; last step (sigma_to = 0) is deterministic and returns x - sigma eps
+    x = torch.randn(1, 4, 8, 8, generator=g).double() * float(s[0])
+    t_last = e.timesteps[-1]
+    assert torch.allclose(e.step(eps, t_last, x).prev_sample, x - s[-2] * eps, atol=1e-6)
