@@ -159,8 +159,8 @@ def test_product_ddim_matches_oracle_ddim():
     ts = torch.tensor([300])
     assert torch.allclose(a.add_noise(x, e, ts), b.add_noise(x, e, ts))
     assert a.init_noise_sigma == 1.0 and a.scale_model_input(x, 3) is x
-    with pytest.raises(NotImplementedError):
-        psched.create_noise_scheduler("euler_a")
+    with pytest.raises(ValueError):        # model_util.py:276-277: unknown names raise ValueError
+        psched.create_noise_scheduler("dpm++")
 
 
 # ---------------------------------------------------------------------------------------- multi-rank fan-out (gloo)
