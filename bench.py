@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """bench.py — SDXL UNet conditioned-forward passes/sec (rank-4 LoRA, 1024 px) on 1..8 B200s.
 
-Workload (BASELINE.json metric): SDXL-base UNet, synthetic seeded weights (no checkpoint is
-reachable offline), rank-4 alpha-1 LoRA on the `noxattn` + `c3lier` leaf set (346 adaptors, lora_up != 0,
-multiplier 1), latents [B,4,128,128] (1024 px), text embeddings [B,77,2048], pooled [B,1280], time ids
-[1024,1024,0,0,1024,1024], timestep 500.  One *step* = one UNet forward over B conditioned passes per GPU
-(B = 8: the reference's per-iteration fan-out of 4 predictions x CFG pair, train_lora_xl.py:236-322).
+Workload (BASELINE.json metric): SDXL-base UNet, synthetic seeded weights (no checkpoint is reachable
+offline), rank-4 alpha-1 LoRA on the `noxattn` + `c3lier` leaf set (346 adaptors, lora_up != 0, multiplier 1), latents
+[B,4,128,128] (1024 px), text embeddings [B,77,2048], pooled [B,1280], time ids [1024,1024,0,0,1024,1024], timestep 500.
+One *step* = one UNet forward over B conditioned passes per GPU (B = 8: the reference's per-iteration fan-out of
+4 predictions x CFG pair, train_lora_xl.py:236-322).
 
-  value     passes/s over all ranks, inputs resident in HBM, CUDA-graph replay of the whole forward,
-            timed with CUDA events, max over ranks.
-  e2e       the same metric through the public call (`sliders_b200.train_util.predict_noise_xl`, the
-            reference's `unet(...)` call site + CFG combine) with HOST (pinned) input buffers: H2D of latents and
-            embeddings and D2H of the guided eps are inside the timed region, every step.
-  roofline  tensor-bound: algorithmic FLOPs of the dominant kernel (`gemm_kernel`: every Linear / conv as
-            tcgen05 GEMM) / its device time, measured live with CUDA events around each launch of one
-            instrumented forward; peak = MEASURED_PEAKS.json bf16_tflops_sustained.
-  cpu_baseline  the oracle (fp32 PyTorch restatement of the diffusers UNet, oracle/unet.py) on the host cores,
-            rank 0, N=1 only, bounded sample.
-`--impl reference`: the reference's own (CPU) implementation cannot run here (diffusers is not installable and
-the trainers hard-code CUDA/xformers), so this arm times the oracle port on all host cores (kind "port").
+  value     passes/s over all ranks, inputs resident in HBM, CUDA-graph replay of the whole forward, timed with CUDA
+            events on the launching stream, max over ranks.
+  e2e       the same metric through the public call (`sliders_b200.train_util.predict_noise_xl`, the reference's
+            `unet(...)` call site + CFG combine) with HOST (pinned) input buffers: H2D of latents and embeddings and D2H
+            of the guided eps are inside the timed region, every step.
+  roofline  tensor-bound.  The launches of one forward are recorded while the forward's CUDA graph is captured and
+            re-captured per kernel class (gemm_kernel = every Linear / conv; attention; norms; the rest) as graphs of
+            their own on the same buffers; each class graph is replayed and timed with CUDA events like the forward.
+            achieved = algorithmic FLOPs of the gemm_kernel launches / their time; peak = MEASURED_PEAKS.json
+            bf16_tflops_sustained.  (Round 1 bracketed eager launches with events, which counted host launch jitter.)
+  configs   the other BASELINE.json configurations (extra keys, the headline is unchanged): SD-1.5 bf16 at
+            B in {1, 2, 8} (config 2), the sharded text-slider iteration (config 3, `train`), the rank-8 image-slider
+            step (config 4), a bounded sample of the 50-step x 11-scale x batch-16 inference sweep (config 5) and, on the
+            host cores, one SD-1.5 text-slider iteration in fp32 (config 1).
+  cpu_baseline  the reference's CPU path for the headline workload on the host cores (rank 0, N = 1), bounded sample.
+`--impl reference`: times that CPU path alone — the reference's unmodified `train_util.predict_noise_xl` + `lora.py`
+hook on the fp32 oracle UNet where /root/reference exists (kind "reference"), else the port of the same code in
+oracle/port.py (kind "port"; the GPU box has no /root/reference and diffusers is not installable anywhere here).
 """
 from __future__ import annotations
 
@@ -36,11 +42,13 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_PASS = 6.761e12          # SURVEY.md §8d, SDXL @128x128 (LoRA r=4 adds 0.0189e12)
-FLOPS_LORA_R4 = 0.0189e12
+FLOPS_PER_PASS = {"sdxl": 6.761e12, "sd15": 0.803e12}      # SURVEY.md §8d / BASELINE.md §2
+FLOPS_LORA = {("sdxl", 4): 0.0189e12, ("sdxl", 8): 0.0378e12, ("sd15", 4): 0.0038e12}
 METRIC = "SDXL UNet conditioned-fwd passes/sec (rank-4 LoRA, 1024px)"
 UNIT = "passes/s"
-LATENT = 128
+LATENT = {"sdxl": 128, "sd15": 64}
+CTX_DIM = {"sdxl": 2048, "sd15": 768}
+KERNEL_CLASS = {"gemm": "gemm", "conv3x3": "gemm", "attention": "attention", "groupnorm": "norm", "layernorm": "norm"}
 
 
 def host_threads() -> int:
@@ -133,83 +141,195 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-def build_product(dev, batch, seed=0):
+def build_product(dev, arch="sdxl", rank=4, seed=0, share=None):
+    """UNet (seeded synthetic weights, or the parameters of `share`) + LoRANetwork(noxattn, c3lier) with lora_up != 0."""
     from sliders_b200 import lora as plora
     from sliders_b200 import synthetic
     from sliders_b200.unet import UNet2DConditionModel, UNetConfig
 
-    with torch.device(dev):
-        unet = UNet2DConditionModel(UNetConfig.sdxl()).to(torch.bfloat16)
-    synthetic.init_synthetic_(unet, seed=seed + 1)
+    cfg = UNetConfig.sdxl() if arch == "sdxl" else UNetConfig.sd15()
+    if share is not None:
+        with torch.device("meta"):
+            unet = UNet2DConditionModel(cfg).to(torch.bfloat16)
+        unet.load_state_dict(share.state_dict(), assign=True)   # same storage: 5 GB are not duplicated
+    else:
+        with torch.device(dev):
+            unet = UNet2DConditionModel(cfg).to(torch.bfloat16)
+        synthetic.init_synthetic_(unet, seed=seed + 1)
     unet.requires_grad_(False)
     unet.eval()
     saved = list(plora.DEFAULT_TARGET_REPLACE)
     plora.DEFAULT_TARGET_REPLACE += plora.UNET_TARGET_REPLACE_MODULE_CONV  # c3lier (train_lora_xl.py:50-52)
     try:
-        net = plora.LoRANetwork(unet, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, torch.bfloat16)
+        net = plora.LoRANetwork(unet, rank=rank, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, torch.bfloat16)
     finally:
         del plora.DEFAULT_TARGET_REPLACE[len(saved):]
     synthetic.init_lora_nonzero_(net, seed=seed + 2, up_std=0.02)
     return unet, net
 
 
-def make_host_inputs(batch, seed=0, pin=True):
+def make_host_inputs(batch, arch="sdxl", seed=0, pin=True):
     g = torch.Generator().manual_seed(seed)
-    lat = torch.randn(batch, 4, LATENT, LATENT, generator=g)
-    ehs = torch.randn(batch, 77, 2048, generator=g).to(torch.bfloat16)
+    n = LATENT[arch]
+    lat = torch.randn(batch, 4, n, n, generator=g)
+    ehs = torch.randn(batch, 77, CTX_DIM[arch], generator=g).to(torch.bfloat16)
     pooled = torch.randn(batch, 1280, generator=g).to(torch.bfloat16)
-    tids = torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]] * batch)
+    tids = torch.tensor([[8.0 * n, 8.0 * n, 0., 0., 8.0 * n, 8.0 * n]] * batch)
     ts = [lat, ehs, pooled, tids]
     if pin and torch.cuda.is_available():
         ts = [t.pin_memory() for t in ts]
     return ts
 
 
-def run_cpu_oracle(state_dict_cpu_f32, lora_fold, n_timed, threads, batch=1, seed=0):
-    """Times the fp32 oracle UNet forward on the host cores.  Returns (passes_per_s, eps) for parity."""
+def timed(fn, steps, warmup, dist_mod=None, sampler=None):
+    """ms per call of `fn`, CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_mod is not None:
+        dist_mod.barrier()
+    if sampler is not None:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_mod is not None:
+        dist_mod.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist_mod is not None:
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+    return t.item() / steps
+
+
+def class_timings(unet, call, steps, warmup):
+    """Records the C-ABI calls of one forward while its CUDA graph is captured, re-captures them per kernel class and
+    times each class graph.  Returns ({class: {"ms", "launches", "flops"}}, kernels per forward)."""
+    from sliders_b200 import ops
+
+    ops.record_calls = []
+    ops.launch_count = 0
+    unet.use_cuda_graph = True
+    call()                                   # first graphed call of this shape: warm-up passes + capture
+    torch.cuda.synchronize()
+    calls, ops.record_calls = ops.record_calls, None
+    n_capture_passes = 3                     # _CapturedForward: two eager warm-ups + the captured pass
+    launches = ops.launch_count // n_capture_passes
+    groups = {}
+    for c in calls:
+        groups.setdefault(KERNEL_CLASS.get(c[2], "other"), []).append(c)
+    out = {}
+    for cls, cl in groups.items():
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ops.replay_calls(cl)
+        ms = timed(g.replay, steps, warmup)
+        out[cls] = {"ms": ms, "launches": len(cl), "flops": sum(c[3] for c in cl)}
+    return out, launches
+
+
+# ---------------------------------------------------------------------------------------------------- CPU legs
+def cpu_pair_call(arch="sdxl", rank=4, seed=0):
+    """The reference's CPU path for one CFG-pair call of the headline workload: `predict_noise_xl` with the LoRA hook
+    live on the fp32 oracle UNet.  Returns (callable -> eps, kind, description)."""
+    from oracle import reference_bridge as rb
     from oracle import unet as ounet
+    from sliders_b200 import synthetic
+
+    xl = arch == "sdxl"
+    cfg = ounet.UNetConfig.sdxl() if xl else ounet.UNetConfig.sd15()
+    with torch.device("meta"):
+        om = ounet.UNet2DConditionModel(cfg)
+    om = om.to_empty(device="cpu")
+    om.load_state_dict({k: synthetic.synthetic_tensor(k, p.shape, seed + 1, "cpu") for k, p in om.named_parameters()},
+                       assign=True)
+    om.requires_grad_(False)
+    om.eval()
+    if rb.available():
+        lora, tu, mu = rb.load("lora"), rb.load("train_util"), rb.load("model_util")
+        saved = list(lora.DEFAULT_TARGET_REPLACE)
+        lora.DEFAULT_TARGET_REPLACE += lora.UNET_TARGET_REPLACE_MODULE_CONV
+        try:
+            net = lora.LoRANetwork(om, rank=rank, multiplier=1.0, alpha=1.0, train_method="noxattn")
+        finally:
+            del lora.DEFAULT_TARGET_REPLACE[len(saved):]
+        sched = mu.create_noise_scheduler("ddim")
+        predict_xl, predict, kind = tu.predict_noise_xl, tu.predict_noise, "reference"
+        what = ("the reference's unmodified trainscripts/textsliders/train_util.py + lora.py (LoRA hook live) on the fp32 "
+                "oracle UNet (oracle/unet.py = diffusers 0.20.2 restated; diffusers itself is not installable)")
+    else:
+        from oracle import ddim as oddim
+        from oracle import port
+
+        net = port.LoRAHooks(om, rank=rank, alpha=1.0, c3lier=True)
+        sched = oddim.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                    num_train_timesteps=1000, clip_sample=False)
+        predict_xl, predict, kind = port.predict_noise_xl, port.predict_noise, "port"
+        what = ("oracle/port.py (port of the reference's train_util.py + lora.py hook, pinned against them in "
+                "tests/test_oracle.py) on the fp32 oracle UNet; /root/reference is absent on this box")
+    synthetic.init_lora_nonzero_(net, seed=seed + 2, up_std=0.02)
+    sched.set_timesteps(1000)
+    lat, ehs, pooled, tids = make_host_inputs(2, arch, seed=seed, pin=False)
+    lat1 = lat[:1].to(torch.bfloat16).float()
+
+    def call():
+        with torch.no_grad(), net:
+            if xl:
+                return predict_xl(om, sched, 500, lat1, ehs.float(), pooled.float(), tids, guidance_scale=3.0)
+            return predict(om, sched, 500, lat1, ehs.float(), guidance_scale=3.0)
+
+    return call, kind, what, (lat1, ehs, pooled, tids)
+
+
+def run_cpu_arm(steps, warmup, budget_s, threads):
+    call, kind, what, _ = cpu_pair_call("sdxl")
+    torch.set_num_threads(threads)
+    times, t_start = [], time.time()
+    for i in range(warmup + steps):
+        t0 = time.time()
+        call()
+        if i >= warmup:
+            times.append(time.time() - t0)
+        if time.time() - t_start > budget_s and times:
+            break
+    return times, kind, what
+
+
+def cpu_config1(threads):
+    """BASELINE config 1: one SD-1.5 text-slider iteration on the host cores, fp32 (timesteps_to fixed to 1: one denoise
+    step + 4 CFG-pair predictions = 10 passes forward, one backward, one AdamW step)."""
+    from oracle import ddim as oddim
+    from oracle import port
+    from oracle import unet as ounet
+    from sliders_b200 import synthetic
 
     torch.set_num_threads(threads)
     with torch.device("meta"):
-        om = ounet.UNet2DConditionModel(ounet.UNetConfig.sdxl())
+        om = ounet.UNet2DConditionModel(ounet.UNetConfig.sd15())
     om = om.to_empty(device="cpu")
-    om.load_state_dict(state_dict_cpu_f32, assign=True)
+    om.load_state_dict({k: synthetic.synthetic_tensor(k, p.shape, 1, "cpu") for k, p in om.named_parameters()}, assign=True)
+    om.requires_grad_(False)
     om.eval()
-    if lora_fold is not None:
-        lora_fold(om)
-    lat, ehs, pooled, tids = make_host_inputs(batch, seed=seed, pin=False)
-    added = {"text_embeds": pooled.float(), "time_ids": tids}
-    with torch.no_grad():
-        t0 = time.time()
-        eps = om(lat.to(torch.bfloat16).float(), 500, ehs.float(), added_cond_kwargs=added).sample  # warm-up
-        warm = time.time() - t0
-        # n_timed is a time budget in seconds when negative: run as many timed calls as fit (1..4)
-        if n_timed < 0:
-            n_timed = int(max(1, min(4, (-n_timed) // max(warm, 1e-3))))
-        times = []
-        for _ in range(n_timed):
-            t0 = time.time()
-            eps = om(lat.to(torch.bfloat16).float(), 500, ehs.float(), added_cond_kwargs=added).sample
-            times.append(time.time() - t0)
-    dt = statistics.mean(times) if times else warm
-    return batch / dt, eps, len(times)
+    net = port.LoRAHooks(om, rank=4, alpha=1.0, c3lier=True)
+    net.__exit__()
+    sched = oddim.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                num_train_timesteps=1000, clip_sample=False)
+    opt = torch.optim.AdamW(net.prepare_optimizer_params(), lr=2e-4)
+    g = torch.Generator().manual_seed(3)
+    emb = {k: torch.randn(1, 77, 768, generator=g) for k in ("target", "positive", "unconditional", "neutral")}
+    lat = torch.randn(1, 4, 64, 64, generator=g)
+    t0 = time.time()
+    loss = port.text_slider_iteration(om, net, sched, opt, emb, lat, timesteps_to=1, guidance_scale=4.0, action="enhance")
+    dt = time.time() - t0
+    return {"what": "SD-1.5 text-slider iteration (train_lora.py:155-309) on the host cores, fp32, rank-4 LoRA (150 adaptors), "
+                    "512 px, timesteps_to = 1: 10 forward passes + backward-to-LoRA + AdamW; oracle/port.py loop",
+            "s_per_iteration": dt, "passes_per_s": 10 / dt, "cores": threads, "loss": float(loss), "kind": "port"}
 
 
-def fold_lora_into(net_state, scales):
-    """Returns f(oracle_model) adding s * up @ down to every adapted leaf (algebraically the LoRA hook)."""
-
-    def fold(om):
-        mods = {("lora_unet_" + n.replace(".", "_")): m for n, m in om.named_modules()}
-        with torch.no_grad():
-            for name, s in scales.items():
-                up = net_state[name + ".lora_up.weight"].float()
-                down = net_state[name + ".lora_down.weight"].float()
-                delta = torch.einsum("or,rikl->oikl", up[:, :, 0, 0], down) if down.dim() == 4 else up @ down
-                mods[name].weight.add_(delta * s)
-
-    return fold
-
-
+# ---------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,17 +338,18 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="conditioned passes per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=25.0)
-    ap.add_argument("--no-train", action="store_true", help="skip the text-slider training-iteration timing")
+    ap.add_argument("--cpu-seconds", type=float, default=30.0)
+    ap.add_argument("--no-train", action="store_true", help="skip the training-iteration timings (configs 3 and 4)")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 1, 2 and 5")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(min(args.warmup, 1), 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     peaks = load_peaks()
     config = {"workload": f"sdxl_unet_fwd_{args.batch}passes_per_gpu_1024px_lora_r4_noxattn_c3lier",
-              "latent": [args.batch, 4, LATENT, LATENT], "timestep": 500, "lora": "rank4 alpha1 noxattn+c3lier (346)",
+              "latent": [args.batch, 4, 128, 128], "timestep": 500, "lora": "rank4 alpha1 noxattn+c3lier (346)",
               "parallelism": f"dp{world} (independent passes, weights replicated, no data-path collective)",
               "l2": "working set (5.1 GB bf16 weights + activations) >> 126 MB L2; no flush needed"}
 
@@ -237,138 +358,79 @@ def main():
         if rank != 0:
             return
         threads = host_threads()
-        from sliders_b200 import synthetic
-        from oracle import unet as ounet
-        with torch.device("meta"):
-            om = ounet.UNet2DConditionModel(ounet.UNetConfig.sdxl())
-        sd = {k: synthetic.synthetic_tensor(k, p.shape, 1, "cpu") for k, p in om.named_parameters()}
-        # bounded sample: one conditioned pass per step (same model / resolution / inputs as the GPU arm)
-        torch.set_num_threads(threads)
-        om = om.to_empty(device="cpu")
-        om.load_state_dict(sd, assign=True)
-        om.eval()
-        lat, ehs, pooled, tids = make_host_inputs(1, pin=False)
-        added = {"text_embeds": pooled.float(), "time_ids": tids}
-        times = []
-        budget_s = 200.0
-        t_start = time.time()
-        with torch.no_grad():
-            for i in range(args.warmup + args.steps):
-                t0 = time.time()
-                om(lat.to(torch.bfloat16).float(), 500, ehs.float(), added_cond_kwargs=added)
-                dt = time.time() - t0
-                if i >= args.warmup:
-                    times.append(dt)
-                if time.time() - t_start > budget_s and len(times) >= 1:
-                    break
+        times, kind, what = run_cpu_arm(args.steps, args.warmup, budget_s=240.0, threads=threads)
         ms = 1e3 * statistics.mean(times)
-        v = 1e3 / ms
-        sample = (f"{len(times)} timed single-pass forwards (B=1) of the same SDXL@128x128 workload, fp32, "
-                  f"{threads} threads; LoRA delta omitted (0.3% of FLOPs)")
+        v = 2.0 * 1e3 / ms                       # a CFG-pair call is two conditioned passes
+        sample = (f"{len(times)} timed CFG-pair calls (predict_noise_xl, batch 1 = 2 passes each, guidance 3, rank-4 LoRA "
+                  f"hook live) of the same SDXL@128x128 workload, fp32, {threads} threads, 240 s budget "
+                  f"({args.steps} requested); {what}")
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-                          "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": config,
-                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                           "sample": sample},
+                          "steps": len(times), "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
     # ------------------------------------------------------------------ our arm
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the sliders_b200 path has no CPU fallback "
-                         "(use --impl reference for the CPU oracle timing)")
+                         "(use --impl reference for the CPU timing)")
     import torch.distributed as dist
-    from sliders_b200 import ops, train_util
+    from sliders_b200 import generate, ops, parallel, train_util, trainer
     from sliders_b200.scheduler import create_noise_scheduler
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    dm = dist if world > 1 else None
     B = args.batch
-    unet, net = build_product(dev, B)
-    lat_h, ehs_h, pooled_h, tids_h = make_host_inputs(B, seed=rank)
-    lat = lat_h.to(dev)
-    ehs = ehs_h.to(dev)
+    unet, net = build_product(dev, "sdxl", 4)
+    lat_h, ehs_h, pooled_h, tids_h = make_host_inputs(B, "sdxl", seed=rank)
+    lat, ehs = lat_h.to(dev), ehs_h.to(dev)
     added = {"text_embeds": pooled_h.to(dev), "time_ids": tids_h.to(dev)}
+    fwd = lambda: unet(lat, 500, ehs, added_cond_kwargs=added).sample
 
-    # launches per forward (eager, counted by the op wrappers) + per-kernel roofline pass
+    # ---- per-kernel-class graphs (also captures the whole-forward graph used below)
     net.__enter__()  # multiplier = 1 (lora.py:252-254)
     with torch.no_grad():
-        unet(lat, 500, ehs, added_cond_kwargs=added)  # packs weights, fills TMA descriptor cache
-        torch.cuda.synchronize()
-        ops.launch_count = 0
-        ops.profile_log = []
-        unet(lat, 500, ehs, added_cond_kwargs=added)
-        torch.cuda.synchronize()
-        log, ops.profile_log = ops.profile_log, None
-        launches_per_fwd = ops.launch_count
-    per_kind = {}
-    for name, fl, e0, e1 in log:
-        d = per_kind.setdefault(name, [0.0, 0.0, 0])
-        d[0] += e0.elapsed_time(e1)
-        d[1] += fl
-        d[2] += 1
-    gemm_ms = per_kind.get("gemm", [0, 0, 0])[0] + per_kind.get("conv3x3", [0, 0, 0])[0]
-    gemm_fl = per_kind.get("gemm", [0, 0, 0])[1] + per_kind.get("conv3x3", [0, 0, 0])[1]
-    gemm_n = per_kind.get("gemm", [0, 0, 0])[2] + per_kind.get("conv3x3", [0, 0, 0])[2]
-    total_ms_eager = sum(v[0] for v in per_kind.values())
-    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    # DRAM traffic of the dominant kernel: from the committed ncu capture of the same workload (profiles/), per launch
+        classes, launches_per_fwd = class_timings(unet, fwd, args.steps, args.warmup)
+
+        # ---- value: graph replay of the whole forward, inputs resident
+        sampler = ClockSampler(local_rank)
+        ms_step = timed(fwd, args.steps, args.warmup, dm, sampler)
+        clocks = sampler.stop()
+    value = world * B / (ms_step * 1e-3)
+    gm = classes.get("gemm", {"ms": 0.0, "launches": 0, "flops": 0.0})
+    achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
     traffic, traffic_note = None, None
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_b8.json")) as f:
+    try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this workload
+        with open(os.path.join(ROOT, "profiles", "r02_dram_b8.json")) as f:
             dj = json.load(f)["per_kernel"]["gemm_kernel"]
         if B == 8:
             traffic = dj["dram_read_bytes_per_launch"] + dj["dram_write_bytes_per_launch"]
-            traffic_note = ("bytes per gemm_kernel launch (mean over the 493 launches of one 8-pass forward), ncu "
-                            "dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_dram_b8_ncu.csv; algorithmic "
-                            "A + W + out (+ residual) bytes per launch: 105.5e6")
+            traffic_note = dj.get("note")
     except (OSError, KeyError, ValueError):
         pass
+    sum_ms = sum(c["ms"] for c in classes.values())
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 GEMM / implicit-GEMM conv)",
                 "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["sustained"], "traffic": traffic, "traffic_note": traffic_note,
-                "peak_source": peaks["source"],
-                "launches": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
-                "share_of_step": gemm_ms / total_ms_eager if total_ms_eager else None,
-                "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(per_kind.items())},
-                "whole_forward_frac": None}
-
-    # ---- value: graph replay, inputs resident
-    unet.use_cuda_graph = True
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            out = unet(lat, 500, ehs, added_cond_kwargs=added).sample
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(args.steps):
-            out = unet(lat, 500, ehs, added_cond_kwargs=added).sample
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
-    value = world * B / (ms_step * 1e-3)
-    roofline["whole_forward_frac"] = (value / world) * (FLOPS_PER_PASS + FLOPS_LORA_R4) / 1e12 / peaks["sustained"]
+                "peak_source": peaks["source"], "launches": gm["launches"],
+                "avg_launch_us": 1e3 * gm["ms"] / max(gm["launches"], 1),
+                "share_of_step": gm["ms"] / ms_step,
+                "breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(classes.items())},
+                "breakdown_sum_ms": round(sum_ms, 3),
+                "how": "per-class CUDA graphs re-captured from the forward's recorded launches, CUDA-event timed "
+                       f"({args.steps} replays each)",
+                "whole_forward_frac": (value / world) * (FLOPS_PER_PASS["sdxl"] + FLOPS_LORA[("sdxl", 4)]) / 1e12 / peaks["sustained"]}
 
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region
     sched = create_noise_scheduler("ddim")
     sched.set_timesteps(1000)
-    eps_host = torch.empty(B // 2 if B > 1 else 1, 4, LATENT, LATENT, dtype=torch.float32).pin_memory()
     half = max(B // 2, 1)
+    eps_host = torch.empty(half, 4, 128, 128, dtype=torch.float32).pin_memory()
 
     def e2e_step():
         # CFG-pair call exactly like the trainers': latents [half], embeddings [2*half] (uncond ; cond)
@@ -380,36 +442,44 @@ def main():
         eps_host[:half].copy_(eps, non_blocking=True)
 
     with torch.no_grad():
-        for _ in range(args.warmup):
-            e2e_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        e0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        e1.record()
-        torch.cuda.synchronize()
-    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_ms = t2.item() / args.steps
-    e2e_passes = 2 * half
+        e2e_ms = timed(e2e_step, args.steps, args.warmup, dm)
     h2d = (lat_h[:half].numel() * 4 + ehs_h[:2 * half].numel() * 2 + pooled_h[:2 * half].numel() * 2
            + tids_h[:2 * half].numel() * 4)
-    d2h = eps_host[:half].numel() * 4
-    e2e = {"value": world * e2e_passes / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+    e2e = {"value": world * 2 * half / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": eps_host[:half].numel() * 4, "ms_per_step": e2e_ms,
            "api": "sliders_b200.train_util.predict_noise_xl (CFG pair, guidance 3) with pinned host buffers"}
+
+    extra = {}
+    # ---- BASELINE config 5 (N = 1): inference sweep, 50 DDIM steps, batch 16 (32 passes per step), slider scales
+    if world == 1 and not args.no_extra:
+        scales = (-5.0, 5.0)
+        g5 = torch.Generator().manual_seed(5)
+        lat16 = torch.randn(16, 4, 128, 128, generator=g5).to(dev, torch.bfloat16)
+        pe = torch.randn(32, 77, 2048, generator=g5).to(dev, torch.bfloat16)
+        ae = torch.randn(32, 1280, generator=g5).to(dev, torch.bfloat16)
+        at = torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]] * 32, device=dev)
+        s5 = create_noise_scheduler("ddim")
+        sweep = lambda sc, n: generate.scale_sweep(unet, net, s5, lat16, pe, ae, at, scales=sc, num_inference_steps=n,
+                                                   guidance_scale=5.0, start_noise=750)
+        with torch.no_grad():
+            sweep((1.0,), 2)                 # captures the two 32-pass graphs (adaptors gated off / on)
+            ms5 = timed(lambda: sweep(scales, 50), 1, 0)
+        per_scale_s = ms5 * 1e-3 / len(scales)
+        extra["config5_inference_sweep"] = {
+            "what": "eval denoise loop (generate_images_xl.py:325-364): batch 16, CFG 5, 50 DDIM steps, slider gated on "
+                    "t <= 750; timed sample = scales (-5, +5) of the 11 of the sweep (-5..+5), same graphs serve every scale",
+            "images_per_s": 16 / per_scale_s, "s_per_scale": per_scale_s, "full_sweep_s_extrapolated": 11 * per_scale_s,
+            "passes_per_s": 32 * 50 / per_scale_s,
+            "frac_of_sustained": 32 * 50 / per_scale_s * (FLOPS_PER_PASS["sdxl"] + FLOPS_LORA[("sdxl", 4)]) / 1e12 / peaks["sustained"]}
+        del lat16, pe, ae, at
     net.__exit__(None, None, None)
 
-    # ---- training path: whole text-slider iterations (train_lora_xl.py:162-356) through sliders_b200.trainer —
-    # partial denoise (25 of 50 DDIM steps, CFG pair, graph replays) + 3 frozen predictions + the grad-carrying one +
-    # backward-to-LoRA + fused AdamW.  Under torchrun the four predictions are sharded one per rank (BASELINE config 3).
+    # ---- training paths: BASELINE config 3 (text slider, one condition per GPU + one LoRA-grad all-reduce) and
+    # config 4 (image slider, rank 8, +scale / -scale on rank parity); whole iterations through sliders_b200.trainer
     train = None
     if not args.no_train:
-        from sliders_b200 import trainer
         net.requires_grad_(True)
+        parallel.broadcast_lora_params(net)
         opt = train_util.get_optimizer("AdamW")(net.prepare_optimizer_params(), lr=2e-4)
         gtr = torch.Generator().manual_seed(77)
         mk = lambda: trainer.PromptEmbedsXL(torch.randn(1, 77, 2048, generator=gtr).to(dev, torch.bfloat16),
@@ -419,58 +489,105 @@ def main():
                                         trainer.PromptSettings(guidance_scale=4.0, resolution=1024, batch_size=1,
                                                                action="enhance"))
         tsched = create_noise_scheduler("ddim")
-        n_it = 2
-        ops.launch_count = 0
-        for it in range(1 + n_it):
-            if it == 1:
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                ops.launch_count = 0
-                e0.record()
-            loss = trainer.text_slider_step_xl(unet, net, tsched, opt, None, pair, timesteps_to=25, device=dev,
-                                               weight_dtype=torch.bfloat16,
-                                               generator=torch.Generator().manual_seed(1000 + it))
-        e1.record()
-        torch.cuda.synchronize()
-        t3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-        it_ms = t3.item() / n_it
+        state = {"it": 0, "loss": None}
+
+        def text_it():
+            state["loss"] = trainer.text_slider_step_xl(unet, net, tsched, opt, None, pair, timesteps_to=25, device=dev,
+                                                        weight_dtype=torch.bfloat16,
+                                                        generator=torch.Generator().manual_seed(1000 + state["it"]))
+            state["it"] += 1
+
+        n_it = 3
+        it_ms = timed(text_it, n_it, 1, dm)
+        parallel.assert_replicas_equal(list(net.parameters()))
         passes = 2 * (25 + 4)  # CFG pairs: 25 denoise steps + positive / neutral / unconditional / target
-        train = {"what": "text-slider iteration, SDXL 1024 px, batch 1, rank-4 LoRA (train_lora_xl.py:162-356): 25 DDIM "
-                         "denoise steps (guidance 3) + 4 CFG-pair predictions + backward-to-LoRA + AdamW(692 tensors)",
+        train = {"what": "BASELINE config 3 — text-slider iteration, SDXL 1024 px, batch 1, rank-4 LoRA "
+                         "(train_lora_xl.py:162-356): 25 DDIM denoise steps (guidance 3) + 4 CFG-pair predictions + "
+                         "backward-to-LoRA + AdamW(692 tensors)",
                  "ms_per_iteration": it_ms, "iterations_timed": n_it, "passes_per_iteration": passes,
-                 "passes_per_s": passes / (it_ms * 1e-3), "loss": float(loss),
-                 "eager_launches_per_iteration": ops.launch_count // n_it,
+                 "passes_per_s": passes / (it_ms * 1e-3), "loss": float(state["loss"]),
+                 "replicas_equal_after": True,
                  "sharding": ("single GPU" if world == 1 else
                               f"denoise CFG-split over rank parity (1 all-gather of 64 KiB per step), target prediction on rank "
                               f"{world - 1}, frozen predictions over ranks 0..{max(world - 2, 0)}, 1 LoRA-grad all-reduce")}
         net.requires_grad_(False)
         opt = None
+        unet.reset_graphs() if hasattr(unet, "reset_graphs") else None
+
+        # config 4: a rank-8 network on a second module tree that shares the 5 GB of UNet parameters
+        unet8, net8 = build_product(dev, "sdxl", 8, share=unet)
+        unet8.use_cuda_graph = True
+        net8.requires_grad_(True)
+        parallel.broadcast_lora_params(net8)
+        opt8 = train_util.get_optimizer("AdamW")(net8.prepare_optimizer_params(), lr=2e-4)
+        g4 = torch.Generator().manual_seed(4)
+        x_low = torch.randn(1, 4, 128, 128, generator=g4)
+        x_high = x_low + 0.3 * torch.randn(1, 4, 128, 128, generator=g4)
+        st4 = {"l": None}
+
+        def image_it():
+            st4["l"] = trainer.image_slider_step_xl(unet8, net8, tsched, opt8, None, pair, x_low, x_high, 2.0,
+                                                    timesteps_to=20, seed=4, device=dev, weight_dtype=torch.bfloat16)
+
+        im_ms = timed(image_it, n_it, 1, dm)
+        parallel.assert_replicas_equal(list(net8.parameters()))
+        extra["config4_image_slider"] = {
+            "what": "BASELINE config 4 — image-slider step, SDXL, rank-8 LoRA, paired synthetic latents [1,4,128,128] with shared "
+                    "noise (train_lora-scale-xl.py:311-375): 2 grad-carrying CFG-pair predictions (+scale / -scale), 2 "
+                    "backward passes accumulated, AdamW",
+            "ms_per_step": im_ms, "steps_timed": n_it, "loss_high": float(st4["l"][0]), "loss_low": float(st4["l"][1]),
+            "replicas_equal_after": True,
+            "sharding": "single GPU" if world == 1 else "+scale prediction on even ranks, -scale on odd ranks, 1 LoRA-grad "
+                                                        "all-reduce (17.3 MB); batch 1 leaves ranks >= 2 idle"}
+        del unet8, net8, opt8
     unet.use_cuda_graph = False
 
-    # ---- CPU baseline (rank 0, N == 1 only)
+    # ---- BASELINE config 2 (N = 1): SD-1.5, rank 4, 512 px, bf16, B in {1, 2, 8}
+    if world == 1 and not args.no_extra:
+        u15, n15 = build_product(dev, "sd15", 4)
+        u15.use_cuda_graph = True
+        rows = {}
+        with torch.no_grad(), n15:
+            for b in (1, 2, 8):
+                l15, e15, _, _ = make_host_inputs(b, "sd15", seed=b, pin=False)
+                l15, e15 = l15.to(dev), e15.to(dev)
+                ms15 = timed(lambda: u15(l15, 500, e15).sample, args.steps, args.warmup)
+                pps = b / (ms15 * 1e-3)
+                rows[f"B{b}"] = {"ms_per_forward": ms15, "passes_per_s": pps,
+                                 "frac_of_sustained": pps * (FLOPS_PER_PASS["sd15"] + FLOPS_LORA[("sd15", 4)]) / 1e12 / peaks["sustained"]}
+        extra["config2_sd15_bf16"] = {"what": "SD-1.5 UNet forward, rank-4 LoRA (150 adaptors), latents [B,4,64,64], CUDA-graph "
+                                              "replay; 100 % of sustained = 1775 passes/s", **rows}
+        del u15, n15
+
+    # ---- CPU legs (rank 0, N == 1 only): the headline workload's CPU baseline + BASELINE config 1
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        sd = {k: v.detach().float().cpu() for k, v in unet.state_dict().items()}
-        nsd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
-        scales = {l.lora_name: float(l.scale) for l in net.unet_loras}
+        torch.set_num_threads(threads)
         t0 = time.time()
-        # one untimed warm-up, then as many timed single-pass forwards as fit args.cpu_seconds (1..4)
-        pps, eps_cpu, n_timed = run_cpu_oracle(sd, fold_lora_into(nsd, scales), -args.cpu_seconds, threads,
-                                               batch=1, seed=0)
-        # parity of the kernel path against this very oracle run (same weights, same inputs)
-        with torch.no_grad(), net:
-            lat0, ehs0, pooled0, tids0 = make_host_inputs(1, seed=0, pin=False)
-            got = unet(lat0.to(dev).to(torch.bfloat16), 500, ehs0.to(dev),
-                       added_cond_kwargs={"text_embeds": pooled0.to(dev), "time_ids": tids0.to(dev)}).sample
+        call, kind, what, (lat1, ehs2, pooled2, tids2) = cpu_pair_call("sdxl")
+        eps_cpu = call()                      # warm-up
+        times = []
+        while not times or (time.time() - t0 < args.cpu_seconds and len(times) < 3):
+            t1 = time.time()
+            eps_cpu = call()
+            times.append(time.time() - t1)
+        # parity of the kernel path against this very CPU run (same weights, same LoRA, same inputs, same call)
+        net.__enter__()
+        with torch.no_grad():
+            got = train_util.predict_noise_xl(unet, sched, 500, lat1.to(dev), ehs2.to(dev), pooled2.to(dev),
+                                              tids2.to(dev), guidance_scale=3.0)
+        net.__exit__(None, None, None)
         rel = ((got.float().cpu() - eps_cpu).norm() / eps_cpu.norm()).item()
-        cpu_baseline = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{n_timed} timed (+1 warm-up) single-pass fp32 forwards of the same SDXL@128x128 LoRA-r4 workload "
-                                  f"(oracle/unet.py), {threads} torch threads, {time.time() - t0:.0f}s wall incl. build",
-                        "eps_rel_rms_kernels_vs_this_oracle": rel}
+        dt = statistics.mean(times)
+        cpu_baseline = {"value": 2.0 / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                        "sample": f"{len(times)} timed (+1 warm-up) CFG-pair calls (predict_noise_xl, batch 1 = 2 passes, guidance "
+                                  f"3, LoRA hook live) of the same SDXL@128x128 workload, fp32, {threads} torch threads, "
+                                  f"{time.time() - t0:.0f}s wall incl. build; {what}",
+                        "eps_rel_rms_kernels_vs_this_cpu_run": rel}
+        del call
+        if not args.no_extra:
+            extra["config1_sd15_cpu_iteration"] = cpu_config1(threads)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -478,7 +595,7 @@ def main():
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_fwd * args.steps,
                 "launches_per_step": launches_per_fwd, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "train": train}
+                "train": train, "configs": extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -15,6 +15,9 @@ denoising under no_grad) — `sample.grad` stays None.
 """
 from __future__ import annotations
 
+import warnings
+import weakref
+
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -459,6 +462,7 @@ class _TrainCapture:
         self.keys = keys
         self.meta = [(tuple(p.shape), p.dtype) for p in params]
         self.pending = False
+        self.pending_token = None
         stream = torch.cuda.Stream(device=sample.device)
         stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(stream):  # warm-up: weight / LoRA packing caches, transposed weights, TMA descriptors
@@ -557,7 +561,27 @@ def _capture_for(unet, sample, t, ehs, added, out_dtype, params, keys):
             cache.pop(next(iter(cache)))
         cap = _TrainCapture(unet, sample, t, ehs, added, out_dtype, params, keys)
         cache[key] = cap
-    return None if cap.pending else cap
+    if cap.pending and cap.pending_token is not None and cap.pending_token() is None:
+        # the autograd node of the forward that was never back-propagated is gone (exception, loss only logged, skipped
+        # step): its tape is dead, the graphs are free again
+        cap.pending = False
+    if cap.pending:
+        global _warned_pending
+        if not _warned_pending:
+            _warned_pending = True
+            warnings.warn("sliders_b200: a second grad-carrying UNet forward with the same signature ran before the first "
+                          "one's backward; it takes the eager (un-graphed) path.  Release or back-propagate the first "
+                          "prediction to return to CUDA-graph replay.")
+        return None
+    return cap
+
+
+_warned_pending = False
+
+
+class _Token:
+    """Lives in the autograd node's __dict__; a dead weakref to it means the node (and its tape) has been freed."""
+    __slots__ = ("__weakref__",)
 
 
 class _UNetFunction(torch.autograd.Function):
@@ -569,6 +593,8 @@ class _UNetFunction(torch.autograd.Function):
         fctx.cap = _capture_for(unet, sample, t, ehs, added, out_dtype, params, keys)
         if fctx.cap is not None:
             fctx.tape = True
+            fctx.token = _Token()
+            fctx.cap.pending_token = weakref.ref(fctx.token)
             return fctx.cap.run_forward(unet, sample, t, ehs, added)
         out, fctx.tape = forward_train(unet, sample, t, ehs, added, out_dtype)
         return out

@@ -64,6 +64,7 @@ struct Ctx {
   std::mutex mu;
   std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> tmaps;
   bool gemm_attr_set = false;
+  bool gemm_stats_attr_set = false;
   bool attn_attr_set = false;
 };
 

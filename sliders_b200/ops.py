@@ -39,17 +39,50 @@ profile_log = None
 _pending_start = None
 
 
+# Optional call recording (bench.py's per-kernel-class timing): while `record_calls` is a list and the current stream is
+# being captured into a CUDA graph, every C-ABI call is remembered as [fn, args, name, flops].  `replay_calls` re-issues
+# a subset on the current stream (normally under a second capture): same kernels, same buffers (they live in the first
+# graph's memory pool), so a class of kernels can be timed back to back as its own graph.
+record_calls = None
+
+
+class _Recorder:
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+
+        def call(*args):
+            record_calls.append([fn, args, None, 0.0])
+            return fn(*args)
+
+        return call
+
+
+def replay_calls(calls) -> None:
+    stream = _stream()
+    for fn, args, _, _ in calls:
+        assert isinstance(args[1], C.c_void_p), "C-ABI convention: (handle, stream, ...)"
+        _cabi.check(fn(args[0], stream, *args[2:]))
+
+
 def _begin():
     global _pending_start
     if profile_log is not None:
         _pending_start = torch.cuda.Event(enable_timing=True)
         _pending_start.record()
-    return _cabi.load()
+    lib = _cabi.load()
+    if record_calls is not None and torch.cuda.is_current_stream_capturing():
+        return _Recorder(lib)
+    return lib
 
 
 def _count(name: str = "", flops: float = 0.0) -> None:
     global launch_count, _pending_start
     launch_count += _KERNELS_PER_CALL.get(name, 1)
+    if record_calls and record_calls[-1][2] is None:
+        record_calls[-1][2], record_calls[-1][3] = name or "other", flops
     if profile_log is not None and _pending_start is not None:
         end = torch.cuda.Event(enable_timing=True)
         end.record()

@@ -232,6 +232,13 @@ def _adaptor_of(leaf: nn.Module):
     fwd = leaf.__dict__.get("forward")
     owner = getattr(fwd, "__self__", None)
     if owner is not None and hasattr(owner, "lora_down") and hasattr(owner, "lora_up"):
+        inner = getattr(getattr(owner, "org_forward", None), "__self__", None)
+        if inner is not None and hasattr(inner, "lora_down"):
+            # the reference chains `org_forward`, so two networks on one UNet both apply there; the fused kernels carry
+            # one adaptor per leaf — refuse loudly instead of silently dropping the first network
+            raise RuntimeError(f"{getattr(owner, 'lora_name', 'leaf')}: a second LoRANetwork was applied to a UNet that "
+                               "already carries one; merge the sliders' weights or build the second network on another "
+                               "UNet2DConditionModel (parameters can be shared with load_state_dict(assign=True))")
         return owner
     return None
 
@@ -380,6 +387,11 @@ class UNet2DConditionModel(nn.Module):
             raise NotImplementedError("too many adapted leaves fused into one call")
         nz = [s for s in scales if s != 0.0]
         common = nz[0] if all(abs(s - nz[0]) < 1e-12 for s in nz) else None
+        if self._bake_scales:
+            # graph mode with adaptor factors that differ BETWEEN call sites (per-module multipliers, a conv rank clamp
+            # changing alpha / r): the replayed graph has one device-side factor, so here every factor is folded into
+            # the packed up-weights instead and the kernels run with scale 1
+            common = None
         key_leaves = tuple(id(l) for l in leaves)
         pack = self._lora_packs.setdefault(key_leaves, _LoraPack())
         ver = tuple((a.lora_down.weight.data_ptr(), a.lora_down.weight._version, a.lora_up.weight.data_ptr(),
@@ -419,6 +431,7 @@ class UNet2DConditionModel(nn.Module):
         return Lora(pack.down, pack.up, r, group_n, common if common is not None else 1.0)
 
     _capturing = False
+    _bake_scales = False
 
     # ---- forward pieces ------------------------------------------------------------------------------
     def _resnet(self, blk: ResnetBlock2D, x0, x1, emb_act) -> torch.Tensor:
@@ -669,7 +682,10 @@ class _CapturedForward:
         if added is not None:
             self.added = {"text_embeds": added["text_embeds"].to(device=x.device, dtype=BF16).clone(),
                           "time_ids": added["time_ids"].to(device=x.device, dtype=torch.float32).clone()}
-        # per-adaptor effective scale folded into one device scalar: graphs assume a common scale
+        # one decision for the whole graph: a factor common to ALL active adaptors is a device-side scalar (one graph
+        # serves every slider scale); otherwise the factors are baked into the packed weights (and are part of the key)
+        self.bake = unet._lora_signature()[1] is None
+        unet._bake_scales = self.bake
         stream = torch.cuda.Stream(device=x.device)
         stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(stream):
@@ -684,6 +700,7 @@ class _CapturedForward:
                 self.out = unet._forward_impl(self.x, self.t, self.ehs, self.added, out_dtype)
         finally:
             unet._capturing = False
+            unet._bake_scales = False
         self.launches = None
 
     def replay(self, unet: UNet2DConditionModel, x, t, ehs, added):
@@ -697,7 +714,11 @@ class _CapturedForward:
         if unet._slider_scale_dev is not None:
             unet._slider_scale_dev.fill_(1.0 if common is None else common)
         # refresh packed LoRA weights if the optimiser changed them (same storage, so the graph sees them)
-        unet._refresh_lora_packs()
+        unet._bake_scales = self.bake
+        try:
+            unet._refresh_lora_packs()
+        finally:
+            unet._bake_scales = False
         self.graph.replay()
         return self.out.clone()
 

@@ -95,3 +95,22 @@ def test_reference_yaml_files_parse_like_the_reference():
         ours = prompt_util.load_prompts_from_yaml(os.path.join(ref_dir, name), atts)
         ref = rp.load_prompts_from_yaml(os.path.join(ref_dir, name), atts)
         assert [o.model_dump() for o in ours] == [r.dict() for r in ref]
+
+
+def test_eval_sweep_host_logic(tmp_path):
+    """eval-scripts/generate_images_xl.py:445-508 driver pieces: CSV rows, slider-name parsing, seeded start noise."""
+    from sliders_b200 import eval_sweep as es
+
+    rows = es.read_prompts_csv(os.path.join(ROOT, "prompts", "prompts-sample.csv"), from_case=1)
+    assert [r["case_number"] for r in rows] == [1, 2] and rows[0]["seed"] == 54737 and rows[1]["prompt"].startswith("photo")
+    info = es.parse_slider_name("models/ageslider_alpha1.0_rank4_noxattn/ageslider_alpha1.0_rank4_noxattn_last.pt")
+    assert (info["rank"], info["alpha"], info["train_method"], info["network_type"]) == (4, 1.0, "noxattn", "c3lier")
+    assert es.parse_slider_name("x_rank8_full.pt")["train_method"] == "full" and es.parse_slider_name("x.pt")["rank"] == 1
+    a = es.initial_latents(7, 2, 64, 64, 2.0, "cpu", torch.float32)
+    torch.manual_seed(7)
+    assert torch.equal(a, torch.randn(2, 4, 8, 8) * 2.0)      # == generator = torch.manual_seed(seed) + prepare_latents
+    args = es.build_parser().parse_args(["--model_name", "m.pt", "--prompts_path", "p.csv", "--save_path", "o"])
+    assert (args.start_noise, args.rank, args.num_samples, args.ddim_steps) == (750, 4, 1, 50)
+    if rb.available():                                        # the reference's own prompt files have these columns
+        ref = es.read_prompts_csv(os.path.join(rb.REFERENCE_ROOT, "prompts", "prompts-person.csv"))
+        assert len(ref) > 10 and ref[0]["prompt"] == "image of a person"

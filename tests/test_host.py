@@ -639,3 +639,20 @@ def test_stochastic_schedulers_match_oracle_restatement():
     assert d._noise_std(0) == 0.0 and d._noise_std(500) > 0.0
     with pytest.raises(ValueError):
         psched.create_noise_scheduler("plms")
+
+
+def test_second_network_on_one_unet_is_refused():
+    """the reference chains `org_forward`, so two LoRANetworks on one UNet both apply; the fused kernels carry
+    one adaptor per leaf, so the engine must refuse instead of silently dropping the first network."""
+    from sliders_b200 import lora as plora
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    from oracle import unet as ounet
+
+    pm = UNet2DConditionModel(UNetConfig.from_dict(ounet.UNetConfig.tiny_xl().__dict__))
+    plora.LoRANetwork(pm, rank=4, alpha=1.0, train_method="noxattn")
+    assert len(pm._adapted_leaves()) > 0
+    plora.LoRANetwork(pm, rank=4, alpha=1.0, train_method="noxattn")
+    pm.__dict__.pop("_adapted_cache", None)
+    with pytest.raises(RuntimeError, match="second LoRANetwork"):
+        pm._adapted_leaves()

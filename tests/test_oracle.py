@@ -357,3 +357,38 @@ def test_stochastic_sampler_identities():
     x = torch.randn(1, 4, 8, 8, generator=g).double() * float(s[0])
     t_last = e.timesteps[-1]
     assert torch.allclose(e.step(eps, t_last, x).prev_sample, x - s[-2] * eps, atol=1e-6)
+
+
+def test_port_reproduces_the_reference_loop_golden():
+    """oracle/port.py (the CPU port bench.py falls back to where /root/reference is absent) against the fixture the
+    reference's own loop source produced (tests/golden/iter_text_xl.pt): same adaptor set, same loss, same gradients."""
+    import os
+
+    from oracle import port
+    from sliders_b200 import synthetic
+
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "iter_text_xl.pt"))
+    cfg = ounet.UNetConfig.tiny_xl()
+    om = ounet.UNet2DConditionModel(cfg)
+    synthetic.init_synthetic_(om, seed=fx["weight_seed"])
+    om.requires_grad_(False).eval()
+    net = port.LoRAHooks(om, rank=fx["rank"], alpha=fx["alpha"], c3lier=True)
+    assert len(net.unet_loras) == fx["n_lora"]
+    assert {k for k, _ in net.named_parameters()} == set(fx["grads"])
+    synthetic.init_lora_nonzero_(net, seed=fx["lora_seed"], up_std=fx["up_std"], reseed_down=True)
+    net.__exit__()
+    sched = oddim.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                num_train_timesteps=1000, clip_sample=False)
+    opt = torch.optim.AdamW(net.prepare_optimizer_params(), lr=fx["lr"])
+    emb = {k: v[0] for k, v in fx["embeds"].items()}
+    added = {k: (v[1], fx["add_time_ids"]) for k, v in fx["embeds"].items()}
+    loss = port.text_slider_iteration(om, net, sched, opt, emb, fx["latents"], fx["timesteps_to"],
+                                      guidance_scale=fx["settings"]["guidance_scale"], action=fx["settings"]["action"],
+                                      added=added)
+    assert abs(float(loss) - float(fx["loss"])) < 1e-5 * max(1.0, abs(float(fx["loss"])))
+    num = den = 0.0
+    for k, p in net.named_parameters():
+        # (the optimizer step ran after backward; .grad is untouched by it)
+        num += (p.grad - fx["grads"][k].float()).pow(2).sum().item()
+        den += fx["grads"][k].float().pow(2).sum().item()
+    assert (num / den) ** 0.5 < 5e-3   # the fixture stores bf16-rounded gradients

@@ -8,9 +8,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from gpu_exp_fill import t  # noqa: E402
 
-shapes = ((8192, 8192, 8192, 256), (8192, 1280, 1280, 256), (8192, 10240, 1280, 256), (8192, 1280, 5120, 256),
-          (8192, 3840, 1280, 256), (32768, 640, 640, 160), (32768, 5120, 640, 256), (2048, 1280, 1280, 128),
-          (2048, 10240, 1280, 256))
+shapes = ((8192, 1280, 1280, 256), (8192, 10240, 1280, 256), (8192, 1280, 5120, 256),
+          (8192, 3840, 1280, 256), (32768, 640, 640, 256), (32768, 5120, 640, 256), (2048, 1280, 1280, 256),
+          (2048, 10240, 1280, 256), (2048, 1280, 5120, 256), (1024, 1280, 1280, 256))
 if len(sys.argv) > 1:
     shapes = shapes[: int(sys.argv[1])]
 
@@ -35,12 +35,13 @@ for (M, N, K, bn) in shapes:
     us, tf = cublas(M, N, K)
     print(f"M{M} N{N} K{K} cuBLAS (context): {us:7.1f}us {tf:5.0f}TF", flush=True)
     for force, kname in ((0x2000, "single"), (0x1000, "pair  ")):
-        for b in sorted({bn, 128} if bn != 128 else {128, 64}, reverse=True):
-            row = []
-            for debug, dn in ((0, "full"), (3, "noload"), (11, "noload+noepi")):
-                try:
-                    us, tf = t(M, N, K, b, debug, force=force)
-                    row.append(f"{dn} {us:7.1f}us {tf:5.0f}TF")
-                except Exception as e:  # noqa: BLE001
-                    row.append(f"{dn} ERR {str(e)[:30]}")
-            print(f"M{M} N{N} K{K} bn{b} {kname}: " + " | ".join(row), flush=True)
+        row = []
+        for b in (256, 224, 192, 160, 128, 96):
+            if b > bn:
+                continue
+            try:
+                us, tf = t(M, N, K, b, 0, force=force)
+                row.append(f"bn{b} {us:6.1f}us {tf:5.0f}TF")
+            except Exception as e:  # noqa: BLE001
+                row.append(f"bn{b} ERR {str(e)[:30]}")
+        print(f"M{M} N{N} K{K} {kname}: " + " | ".join(row), flush=True)
