@@ -232,7 +232,7 @@ def class_timings(unet, call, steps, warmup):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU legs
-def cpu_pair_call(arch="sdxl", rank=4, seed=0):
+def cpu_pair_call(arch="sdxl", rank=4, seed=0, lora_state=None):
     """The reference's CPU path for one CFG-pair call of the headline workload: `predict_noise_xl` with the LoRA hook
     live on the fp32 oracle UNet.  Returns (callable -> eps, kind, description)."""
     from oracle import reference_bridge as rb
@@ -271,6 +271,10 @@ def cpu_pair_call(arch="sdxl", rank=4, seed=0):
         what = ("oracle/port.py (port of the reference's train_util.py + lora.py hook, pinned against them in "
                 "tests/test_oracle.py) on the fp32 oracle UNet; /root/reference is absent on this box")
     synthetic.init_lora_nonzero_(net, seed=seed + 2, up_std=0.02)
+    if lora_state is not None:   # the kernel path's adaptor weights, so that the two runs compute the same function
+        own = net.state_dict()
+        net.load_state_dict({k: lora_state[k].detach().float().cpu().reshape(own[k].shape) for k in own if k in lora_state},
+                            strict=False)
     sched.set_timesteps(1000)
     lat, ehs, pooled, tids = make_host_inputs(2, arch, seed=seed, pin=False)
     lat1 = lat[:1].to(torch.bfloat16).float()
@@ -565,7 +569,7 @@ def main():
         threads = host_threads()
         torch.set_num_threads(threads)
         t0 = time.time()
-        call, kind, what, (lat1, ehs2, pooled2, tids2) = cpu_pair_call("sdxl")
+        call, kind, what, (lat1, ehs2, pooled2, tids2) = cpu_pair_call("sdxl", lora_state=net.state_dict())
         eps_cpu = call()                      # warm-up
         times = []
         while not times or (time.time() - t0 < args.cpu_seconds and len(times) < 3):

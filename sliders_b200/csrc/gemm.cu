@@ -45,7 +45,8 @@ namespace sb200 {
 
 constexpr int kBM = 128;  // rows per CTA
 constexpr int kBK = 64;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiPerQuarter = kEpiWarps / 4;  // epilogue warps sharing one TMEM lane quarter (32 rows); slabs are dealt round-robin
 constexpr int kProducers = 2;  // TMA producer warps; k-blocks are dealt to them round-robin
 constexpr int kGemmThreads = 32 * (kEpiWarps + kProducers + 1);
 // Warp roles by index: the two single-instruction-stream roles get the HIGHEST warp ids.  A sub-partition's issue arbiter
@@ -62,7 +63,9 @@ constexpr int kBarRegion = 1024;
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // UMMA smem descriptor, high word
 constexpr int kSlab = 32;             // output columns staged per epilogue-warp iteration
 constexpr int kEpiBufBytes = 32 * 64; // [32 rows x 32 cols] bf16
-constexpr int kEpiBytesPerWarp = 2 * kEpiBufBytes;  // + 2 x [32 cols][r] fp32 of lora_up rows when LoRA is fused (p.up_buf_bytes)
+constexpr int kEpiBufs = 1;           // staging buffers per epilogue warp (with 4 warps per lane quarter the other warps of
+                                      // the sub-partition hide a slab's prefetch latency; a second buffer per warp would cost stages)
+constexpr int kEpiBytesPerWarp = kEpiBufs * kEpiBufBytes;  // + kEpiBufs x [32 cols][r] fp32 of lora_up rows when LoRA is fused
 constexpr int kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
 
 struct GemmParams {
@@ -148,6 +151,15 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
       }
     }
   }
+}
+
+// kStats builds write 8 int64 per CTA: {producer wait, producer total, issuer wait on full, issuer total, epilogue warp 0
+// wait on the accumulator, epilogue warp 0 total, issuer wait on the accumulator hand-back, -}.  The buffer travels in
+// the (otherwise unused) rowbias slot of a call without SB200_EPI_ROWBIAS; without one the head of `out` is used.
+__device__ __forceinline__ long long* stats_out(const GemmParams& p) {
+  return (p.rowbias != nullptr && !(p.flags & SB200_EPI_ROWBIAS))
+             ? reinterpret_cast<long long*>(const_cast<__nv_bfloat16*>(p.rowbias))
+             : reinterpret_cast<long long*>(p.out);
 }
 
 // First output pixel (b0, h0, w0) of conv sub-tile `st` (w fastest, then h, then batch).
@@ -361,7 +373,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       }
     }
     if (kStats && lane == 0 && pw == 0) {
-      long long* o = reinterpret_cast<long long*>(p.out) + blockIdx.x * 4;
+      long long* o = stats_out(p) + blockIdx.x * 8;
       o[0] = st_wait;
       o[1] = clock64() - st_t0;
     }
@@ -463,16 +475,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         if (as == 0) aphase ^= 1u;
       }
       if (kStats && lane == 0) {
-        long long* o = reinterpret_cast<long long*>(p.out) + blockIdx.x * 4;
+        long long* o = stats_out(p) + blockIdx.x * 8;
         o[2] = st_wait;
         o[3] = clock64() - st_t0;
-        (void)st_twait;
+        o[6] = st_twait;
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..7, every CTA)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int hsel = warp >> 2;             // which of the two warps of this quarter (slab parity)
+    const int hsel = warp >> 2;             // which of the kEpiPerQuarter warps of this quarter (slab index mod that)
     int as = 0;
     uint32_t aphase = 0;
     const float lscale =
@@ -487,9 +499,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     // (row >> 1) & 3): residual tiles arrive here by cp.async with coalesced global reads, results leave from
     // here with coalesced global writes; in between every thread touches only its own row.
     const uint32_t ebuf = tiles + static_cast<uint32_t>(S) * stage_bytes +
-                          static_cast<uint32_t>(warp) * (kEpiBytesPerWarp + 2 * p.up_buf_bytes);
-    const uint32_t ubuf0 = ebuf + 2 * kEpiBufBytes;  // 2 x p.up_buf_bytes, same double-buffer parity as ebuf
+                          static_cast<uint32_t>(warp) * (kEpiBytesPerWarp + kEpiBufs * p.up_buf_bytes);
+    const uint32_t ubuf0 = ebuf + kEpiBufs * kEpiBufBytes;  // kEpiBufs x p.up_buf_bytes, same buffer parity as ebuf
     int bufsel = 0;
+    long long st_wait = 0;
+    const long long st_t0 = kStats ? clock64() : 0;
     for (int t = unit; t < total_tiles; t += num_units) {
       const int mt = n_fast ? t / num_n_tiles : t % num_m_tiles;
       const int nt = n_fast ? t % num_n_tiles : t / num_m_tiles;
@@ -518,7 +532,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       const int n_base = nt * p.ncols_out;
       const int ncols_valid = min(p.ncols_out, p.Nout - n_base);
       const int nslabs = (ncols_valid + kSlab - 1) / kSlab;
-      const int my_slabs = skip_epi ? 0 : ((nslabs - hsel + 1) >> 1);  // slabs hsel, hsel+2, ...
+      const int my_slabs = skip_epi ? 0 : (nslabs - hsel + kEpiPerQuarter - 1) / kEpiPerQuarter;  // slabs hsel, hsel + kEpiPerQuarter, ...
       auto prefetch_resid = [&](int col0, int sw, uint32_t buf) {
         const int cpr = sw >> 3;  // 16-byte chunks per row
         if (has_resid) {
@@ -546,7 +560,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         prefetch_resid(hsel * kSlab, min(kSlab, ncols_valid - hsel * kSlab), ebuf + bufsel * kEpiBufBytes);
       const __nv_bfloat16* rb =
           (p.flags & SB200_EPI_ROWBIAS) ? p.rowbias + static_cast<size_t>(row_ok ? my_batch : 0) * p.Nout : nullptr;
-      mbar_wait(bar_tfull + 8u * as, aphase);
+      {
+        const long long w0c = kStats ? clock64() : 0;
+        mbar_wait(bar_tfull + 8u * as, aphase);
+        if (kStats) st_wait += clock64() - w0c;
+      }
       tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
@@ -554,12 +572,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       int cur_group = -1;
       const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);
       for (int k = 0; k < my_slabs; ++k) {
-        const int col0 = (hsel + 2 * k) * kSlab;
+        const int col0 = (hsel + kEpiPerQuarter * k) * kSlab;
         const int sw = min(kSlab, ncols_valid - col0);
         const uint32_t buf = ebuf + bufsel * kEpiBufBytes;
         const bool more = k + 1 < my_slabs;
-        if (staged && more) {
-          const int ncol0 = col0 + 2 * kSlab;
+        if (kEpiBufs == 2 && staged && more) {
+          const int ncol0 = col0 + kEpiPerQuarter * kSlab;
           prefetch_resid(ncol0, min(kSlab, ncols_valid - ncol0), ebuf + (bufsel ^ 1) * kEpiBufBytes);
         }
         for (int sub = 0; sub * 16 < sw; ++sub) {
@@ -586,7 +604,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
           if (staged && sub == 0) {  // this slab's residual / lora_up rows have landed (the next slab's copy may be in flight)
-            if (more)
+            if (kEpiBufs == 2 && more)
               cp_async_wait<1>();
             else
               cp_async_wait<0>();
@@ -649,7 +667,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           }
         }
         __syncwarp();
-        bufsel ^= 1;
+        if (kEpiBufs == 2) {
+          bufsel ^= 1;
+        } else if (staged && more) {  // single buffer: the next slab's residual / lora_up rows replace what was just copied out
+          const int ncol0 = col0 + kEpiPerQuarter * kSlab;
+          prefetch_resid(ncol0, min(kSlab, ncols_valid - ncol0), ebuf);
+        }
       }
       if (my_slabs == 0) {  // nothing to read for this warp (narrow last tile): still release the accumulator
         tc_fence_before();
@@ -663,6 +686,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
+    }
+    if (kStats && warp == 0 && lane == 0) {
+      long long* o = stats_out(p) + blockIdx.x * 8;
+      o[4] = st_wait;
+      o[5] = clock64() - st_t0;
     }
   }
 
@@ -701,18 +729,21 @@ static int pair_policy() {
   return v;
 }
 
-// Cost model (SM cycles per launch, fitted to the round-2 same-box measurements in profiles/r02_gemm_tiles.txt).
-// Per 64-deep k-block a CTA needs max(tensor, smem, issue):
-//   tensor  (bn + rt) / 2 cycles per UMMA, 4 UMMAs
-//   smem    every byte of the stage is written by TMA and read back by the tensor core through the same 128 B/clk
-//           port; the pair halves the W / LoRA rows per CTA
-//   issue   ~80 cycles per UMMA incl. the barrier handshake of the converged issue loop
-// and work is dealt in waves over the persistent units.
+// Cost model in SM cycles, fitted to the round-2 same-box measurements (profiles/r02_gemm_matrix_v2_two_producers.log,
+// r02_gemm_stats_two_producers.log: cycles per 64-deep k-block from the kStats build):
+//   CTA pair    max(2 (bn + rt), ~325)      tensor-bound from bn = 176 up, below that the two producer warps' issue
+//               rate (3 TMA instructions per k-block with LoRA: +40)
+//   single CTA  ~390 + (bn + rt) / 2        (524 at 256, 456 at 128, 415 at 64)
+// A tile costs kblocks of those plus ~600 cycles of hand-over; its epilogue (~14 cycles per output column, more with a
+// residual / LoRA / GEGLU) overlaps the next tile's main loop unless it is longer; work is dealt in waves over the
+// persistent units; a launch pays its prologue, the last tile's epilogue and, for the pair, cluster launch / sync.
 static TileChoice pick_tile(int M, int ncols, int max_bn, int step, int num_sms, int kblocks, int lora_rt,
-                            int force_ctas, int sub_tiles) {
+                            int force_ctas, int sub_tiles, int flags) {
   double best = -1;
   TileChoice bc{1, step};
   const int pol = pair_policy();
+  const bool geglu = (flags & SB200_EPI_GEGLU) != 0;
+  const double epi_per_col = 14.0 + ((flags & SB200_EPI_RESID) ? 5.0 : 0.0) + (lora_rt ? 6.0 : 0.0) + (geglu ? 10.0 : 0.0);
   for (int ctas = 1; ctas <= 2; ++ctas) {
     if (force_ctas ? ctas != force_ctas : ((pol == 0 && ctas == 2) || (pol == 2 && ctas == 1))) continue;
     const int m_tiles = (sub_tiles + ctas - 1) / ctas;
@@ -722,15 +753,13 @@ static TileChoice pick_tile(int M, int ncols, int max_bn, int step, int num_sms,
       const int n_tiles = (ncols + bn - 1) / bn;
       const long tiles = static_cast<long>(m_tiles) * n_tiles;
       const long waves = (tiles + units - 1) / units;
-      const double mma = 2.0 * (bn + lora_rt);
-      const double smem = 2.0 * (16384.0 + (bn + lora_rt) * 128.0 / ctas) / 160.0;
-      const double issue = 320.0;
-      double perkb = mma;
-      if (smem > perkb) perkb = smem;
-      if (issue > perkb) perkb = issue;
-      const double epi = 400.0 + bn * 12.0;  // per tile, overlapped with the next tile's main loop
-      const double tile = kblocks * perkb > epi ? kblocks * perkb : epi;
-      const double cost = waves * tile + 4000.0 + epi + (ctas == 2 ? 1500.0 : 0.0);
+      const double wide = 2.0 * (bn + lora_rt);
+      const double perkb = ctas == 2 ? (wide > 325.0 + (lora_rt ? 40.0 : 0.0) ? wide : 325.0 + (lora_rt ? 40.0 : 0.0))
+                                     : 390.0 + 0.25 * wide;
+      const double epi = 400.0 + epi_per_col * (geglu ? bn / 2 : bn);
+      const double main_loop = kblocks * perkb + 600.0;
+      const double tile = main_loop > epi ? main_loop : epi;
+      const double cost = waves * tile + 4000.0 + epi + (ctas == 2 ? 3000.0 : 0.0);
       if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && bn > bc.bn)) {
         best = cost;
         bc = TileChoice{ctas, bn};
@@ -750,7 +779,14 @@ static bool n_fast_default() {
 }
 
 static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
-  p.n_fast = n_fast_default() ? 1 : 0;
+  // Tile order: N fastest reads each A row-tile from DRAM once and re-reads W once per row-tile, which is free while W
+  // stays in L2.  When W is the big operand and does not fit (the batched cross-attention K/V projection: 616 x 2048
+  // activations against 629 MB of weights) the M-fastest order streams W once instead.
+  {
+    const double w_bytes = 2.0 * p.N * p.K;
+    const double a_bytes_total = 2.0 * p.M * (p.a_mode == 0 ? p.K : p.K / 9);
+    p.n_fast = (n_fast_default() && !(w_bytes > a_bytes_total && w_bytes > 64e6)) ? 1 : 0;
+  }
   // two k-blocks per elect region pays for tiles whose 4 UMMAs (2 (bn + rt) cycles) are shorter than one pass of the
   // issue loop; wide tiles run better with one (same-box A/B, profiles/r02_gemm_tiles.txt)
   static const int unroll_env = env_int("SB200_MMA_UNROLL", -1);
@@ -761,7 +797,7 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
   p.l_rows = has_lora ? p.lora_rt / ctas : 0;
   p.stage_bytes = kBM * 128 + p.b_rows * 128 + p.l_rows * 128;
   p.up_buf_bytes = has_lora ? kSlab * p.lora_r * 4 : 0;
-  const int epi_bytes = kEpiBytes + kEpiWarps * 2 * p.up_buf_bytes;
+  const int epi_bytes = kEpiBytes + kEpiWarps * kEpiBufs * p.up_buf_bytes;
   int stages = (kSmemBudget - kBarRegion - 1024 - epi_bytes) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(SB200_ERR_INVALID, "gemm: tile does not fit shared memory");
@@ -888,7 +924,7 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
   const int step = geglu ? 32 : 16;
   int bn, force_ctas;
   decode_bn(bn_arg, &bn, &force_ctas, &p.debug);
-  TileChoice tc = pick_tile(M, N, max_bn, step, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, force_ctas, p.num_sub);
+  TileChoice tc = pick_tile(M, N, max_bn, step, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, force_ctas, p.num_sub, flags);
   if (bn > 0) tc.bn = bn;
   if (force_ctas) tc.ctas = force_ctas;
   const int need = (tc.ctas == 2 && (has_lora || geglu)) ? 32 : step;
@@ -1016,7 +1052,7 @@ extern "C" int sb200_conv3x3(void* handle, void* stream, const void* x0, int ldx
   }
   int bn, force_ctas;
   decode_bn(bn_arg, &bn, &force_ctas, &p.debug);
-  TileChoice tc = pick_tile(M, Cout, max_bn, 16, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, force_ctas, p.num_sub);
+  TileChoice tc = pick_tile(M, Cout, max_bn, 16, ctx->num_sms, p.kblocks, has_lora ? lora->rt : 0, force_ctas, p.num_sub, flags);
   if (bn > 0) tc.bn = bn;
   if (force_ctas) tc.ctas = force_ctas;
   const int need = (tc.ctas == 2 && has_lora) ? 32 : 16;

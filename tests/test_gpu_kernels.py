@@ -305,8 +305,10 @@ def test_bad_arguments_return_errors_not_crashes(dev):
     w = torch.zeros(64, 60, device=dev, dtype=BF)
     with pytest.raises(_cabi.Sb200Error, match="multiples of 8"):
         ops.gemm(x, w)
-    with pytest.raises(_cabi.Sb200Error, match="must divide 128"):
-        ops.conv3x3(torch.zeros(1, 96, 96, 64, device=dev, dtype=BF), torch.zeros(64, 3, 3, 64, device=dev, dtype=BF))
+    with pytest.raises(_cabi.Sb200Error, match="multiples of 64"):   # channels are the only conv shape constraint left
+        ops.conv3x3(torch.zeros(1, 96, 96, 40, device=dev, dtype=BF), torch.zeros(64, 3, 3, 40, device=dev, dtype=BF))
+    with pytest.raises(_cabi.Sb200Error, match="stride 2 needs even dims"):
+        ops.conv3x3(torch.zeros(1, 9, 9, 64, device=dev, dtype=BF), torch.zeros(64, 3, 3, 64, device=dev, dtype=BF), stride=2)
     with pytest.raises(_cabi.Sb200Error, match="CUDA tensors"):
         ops.layernorm(torch.zeros(4, 64, dtype=BF), torch.zeros(64, dtype=BF), torch.zeros(64, dtype=BF))
 

@@ -171,8 +171,8 @@ if __name__ == "__main__":
         sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         import bench
         nb = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-        unet, net = bench.build_product(dev, nb)
-        lat_h, ehs_h, pooled_h, tids_h = bench.make_host_inputs(nb, pin=False)
+        unet, net = bench.build_product(dev)
+        lat_h, ehs_h, pooled_h, tids_h = bench.make_host_inputs(nb, "sdxl", pin=False)
         args = (lat_h.to(dev), 500, ehs_h.to(dev))
         added = {"text_embeds": pooled_h.to(dev), "time_ids": tids_h.to(dev)}
         with torch.no_grad(), net:

@@ -9,10 +9,10 @@ import bench  # noqa: E402
 
 dev = torch.device("cuda:0")
 batches = [int(a) for a in sys.argv[1:]] or [8]
-unet, net = bench.build_product(dev, max(batches))
+unet, net = bench.build_product(dev)
 unet.use_cuda_graph = True
 for B in batches:
-    lat_h, ehs_h, pooled_h, tids_h = bench.make_host_inputs(B, pin=False)
+    lat_h, ehs_h, pooled_h, tids_h = bench.make_host_inputs(B, "sdxl", pin=False)
     lat, ehs = lat_h.to(dev), ehs_h.to(dev)
     added = {"text_embeds": pooled_h.to(dev), "time_ids": tids_h.to(dev)}
     with torch.no_grad(), net:
@@ -28,4 +28,4 @@ for B in batches:
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     print(f"B={B}: {ms:.2f} ms/forward -> {B / ms * 1e3:.1f} passes/s "
-          f"[SB200_ELECT_ISSUE={os.environ.get('SB200_ELECT_ISSUE', '0')}]", flush=True)
+          f"[SB200_PAIR={os.environ.get('SB200_PAIR', '1')}]", flush=True)
