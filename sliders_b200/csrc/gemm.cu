@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         const int cpr = sw >> 3;  // 16-byte chunks per row
         if (has_resid) {
           for (int idx = lane; idx < 32 * cpr; idx += 32) {
-            const int row = idx / cpr;
+            const int row = cpr == 4 ? idx >> 2 : idx / cpr;
             const int ch = idx - row * cpr;
             const int mr = __shfl_sync(0xffffffffu, my_row, row);
             if (mr >= 0)
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
       float tl[8];
-      int cur_group = -1;
+      int group_lo = 0, group_hi = 0;  // output-column range of the adaptor whose t = A.down^T is held in tl
       const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);
       for (int k = 0; k < my_slabs; ++k) {
         const int col0 = (hsel + kEpiPerQuarter * k) * kSlab;
@@ -587,10 +587,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           uint32_t g[16];
           tmem_ld_x16(taddr + c + ((pair_lora && c >= half_cols) ? lr_half : 0), v);
           if (geglu) tmem_ld_x16(taddr + (bn >> 1) + c, g);
-          if (has_lora) {
+          if (has_lora && (n < group_lo || n >= group_hi)) {
             const int grp = n / p.lora_group_n;
-            if (grp != cur_group) {
-              cur_group = grp;
+            group_lo = grp * p.lora_group_n;
+            group_hi = group_lo + p.lora_group_n;
+            {
               uint32_t tv[8];
               const int j = grp * p.lora_r;
               tmem_ld_x8(taddr + ((pair_lora && j < lr_half) ? half_cols + j : bn + j), tv);
@@ -629,19 +630,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           }
           const uint32_t a0 = buf + lane * 64 + (((2 * sub) ^ swz) << 4);
           const uint32_t a1 = buf + lane * 64 + (((2 * sub + 1) ^ swz) << 4);
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
           if (has_resid && row_ok) {
+            // the residual is added to the ROUNDED projection, in bf16, like the reference's separate elementwise
+            // `hidden_states = attn_output + hidden_states` on two bf16 tensors (8 packed adds instead of 32 fp32 ops)
             const uint4 r0 = ld_shared_v4(a0), r1 = ld_shared_v4(a1);
             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[2 * j] += bf16_lo(rw[j]);
-              f[2 * j + 1] += bf16_hi(rw[j]);
-            }
+            for (int j = 0; j < 8; ++j) o[j] = add_bf16x2(o[j], rw[j]);
           }
-          st_shared_v4(a0, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                      pack_bf16x2(f[6], f[7])));
-          st_shared_v4(a1, make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                                      pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15])));
+          st_shared_v4(a0, make_uint4(o[0], o[1], o[2], o[3]));
+          st_shared_v4(a1, make_uint4(o[4], o[5], o[6], o[7]));
         }
         if (!more) {
           // the accumulator has been read completely: hand it back to the MMA warp before the last copy-out
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         {  // coalesced copy-out of the staged [32 x sw] tile
           const int cpr = sw >> 3;
           for (int idx = lane; idx < 32 * cpr; idx += 32) {
-            const int row = idx / cpr;
+            const int row = cpr == 4 ? idx >> 2 : idx / cpr;
             const int ch = idx - row * cpr;
             const int mr = __shfl_sync(0xffffffffu, my_row, row);
             const uint4 val = ld_shared_v4(buf + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));

@@ -197,7 +197,7 @@ def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
     lib = _begin()
     _cabi.check(lib.sb200_layernorm(_ctx(x), _stream(), _p(x), x.stride(0), _p(gamma), _p(beta), _p(out), Cc, M,
                                     Cc, float(eps)))
-    _count()
+    _count("layernorm")
     return out
 
 
@@ -211,7 +211,7 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias=None, *, act_in: bool = 
     _cabi.check(lib.sb200_small_linear(_ctx(x), _stream(), _p(x), x.stride(0), _p(w), w.stride(0), _p(bias),
                                        _p(out), N, M, N, K, int(act_in), int(act_out),
                                        lora.ref() if lora is not None else None, _p(resid)))
-    _count()
+    _count("small_linear")
     return out
 
 
@@ -221,7 +221,7 @@ def sinusoid(values: torch.Tensor, dim: int) -> torch.Tensor:
     out = torch.empty((n, dim), device=values.device, dtype=BF16)
     lib = _begin()
     _cabi.check(lib.sb200_sinusoid(_ctx(values), _stream(), _p(values), n, dim, _p(out), dim))
-    _count()
+    _count("sinusoid")
     return out
 
 
@@ -234,7 +234,7 @@ def conv_in(latent: torch.Tensor, w_packed: torch.Tensor, bias) -> torch.Tensor:
     lib = _begin()
     _cabi.check(lib.sb200_conv_in(_ctx(latent), _stream(), _p(latent), int(latent.dtype == torch.float32),
                                   _p(w_packed), _p(bias), _p(out), B, H, W, Cout))
-    _count()
+    _count("conv_in")
     return out
 
 
@@ -244,7 +244,7 @@ def conv_out(x: torch.Tensor, w_packed: torch.Tensor, bias, out_dtype=BF16) -> t
     lib = _begin()
     _cabi.check(lib.sb200_conv_out(_ctx(x), _stream(), _p(x), _p(w_packed), _p(bias), _p(out),
                                    int(out_dtype == torch.float32), B, H, W, Cin))
-    _count()
+    _count("conv_out")
     return out
 
 
@@ -253,7 +253,7 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((B, 2 * H, 2 * W, Cc), device=x.device, dtype=BF16)
     lib = _begin()
     _cabi.check(lib.sb200_upsample2x(_ctx(x), _stream(), _p(x), _p(out), B, H, W, Cc))
-    _count()
+    _count("upsample2x")
     return out
 
 
@@ -281,7 +281,7 @@ def cfg_ddim(eps2: torch.Tensor, guidance: float, x: Optional[torch.Tensor] = No
     _cabi.check(fn(_ctx(eps2), _stream(), _p(eps2), int(eps2.dtype == torch.float32),
                                    float(guidance), _p(x), float(a_t), float(a_prev), _p(x_prev), _p(eps_out),
                                    int(out_dtype == torch.float32), n))
-    _count()
+    _count("cfg_ddim")
     return eps_out, x_prev
 
 
