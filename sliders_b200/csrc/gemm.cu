@@ -107,6 +107,16 @@ struct GemmParams {
   int lora_r, lora_rt, lora_group_n;
   float lora_scale;
   const float* lora_scale_dev;
+  // LayerNorm folded into this projection (struct sb200_lnfold) / row statistics left for the next one
+  const float* ln_stats;
+  int ln_parts;
+  float ln_inv_c, ln_eps;
+  const float* ln_c;
+  const float* ln_d;
+  const float* ln_cl;
+  const float* ln_dl;
+  float* rs_out;
+  int rs_parts;
 };
 
 __device__ __forceinline__ void add_bf16x16(float* f, const __nv_bfloat16* src) {
@@ -529,6 +539,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         }
       }
       const bool row_ok = my_row >= 0;
+      // LayerNorm fold: (mean, rstd) of this thread's row of x from the producer's partial sums
+      // part-major [parts][M][2]: the 32 rows of a warp read consecutive addresses.  The first loads are issued here
+      // and summed after the accumulator wait, so their L2 latency hides behind it.
+      constexpr int kLnPre = 8;
+      float2 ln_pre[kLnPre];
+      const bool ln_on = p.ln_stats != nullptr && row_ok;
+      const float2* ln_sp = reinterpret_cast<const float2*>(p.ln_stats) + (ln_on ? my_row : 0);
+#pragma unroll
+      for (int i = 0; i < kLnPre; ++i)
+        ln_pre[i] = (ln_on && i < p.ln_parts) ? __ldg(ln_sp + static_cast<size_t>(i) * p.M) : make_float2(0.f, 0.f);
+      float rs1 = 0.f, rs2 = 0.f;  // row statistics of what this warp writes in this tile
       const int n_base = nt * p.ncols_out;
       const int ncols_valid = min(p.ncols_out, p.Nout - n_base);
       const int nslabs = (ncols_valid + kSlab - 1) / kSlab;
@@ -568,6 +589,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
+      // LayerNorm fold: (mean, rstd) of this thread's row of x from the producer's partial sums
+      float ln_rstd = 1.f, ln_rm = 0.f;
+      if (ln_on) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kLnPre; ++i) {
+          s1 += ln_pre[i].x;
+          s2 += ln_pre[i].y;
+        }
+        for (int i = kLnPre; i < p.ln_parts; ++i) {
+          const float2 v2 = __ldg(ln_sp + static_cast<size_t>(i) * p.M);
+          s1 += v2.x;
+          s2 += v2.y;
+        }
+        const float mean = s1 * p.ln_inv_c;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - mean * mean, 0.f) + p.ln_eps);
+        ln_rm = ln_rstd * mean;
+      }
       float tl[8];
       int group_lo = 0, group_hi = 0;  // output-column range of the adaptor whose t = A.down^T is held in tl
       const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);
@@ -596,14 +635,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
               const int j = grp * p.lora_r;
               tmem_ld_x8(taddr + ((pair_lora && j < lr_half) ? half_cols + j : bn + j), tv);
               tmem_ld_wait();
+              if (p.ln_cl != nullptr) {
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) tl[jj] = __uint_as_float(tv[jj]) * lscale;
+                for (int jj = 0; jj < 8; ++jj)
+                  tl[jj] = (jj < p.lora_r) ? fmaf(__uint_as_float(tv[jj]), ln_rstd,
+                                                  fmaf(-ln_rm, __ldg(p.ln_cl + j + jj), __ldg(p.ln_dl + j + jj))) * lscale
+                                           : 0.f;
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) tl[jj] = __uint_as_float(tv[jj]) * lscale;
+              }
             }
           }
           tmem_ld_wait();
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.ln_stats != nullptr) {
+            // LN(x) . W^T + b = rstd * acc - rstd * mean * c[n] + d[n]
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 cc = __ldg(reinterpret_cast<const float4*>(p.ln_c + n) + j4);
+              const float4 dd = __ldg(reinterpret_cast<const float4*>(p.ln_d + n) + j4);
+              f[4 * j4 + 0] = fmaf(f[4 * j4 + 0], ln_rstd, fmaf(-ln_rm, cc.x, dd.x));
+              f[4 * j4 + 1] = fmaf(f[4 * j4 + 1], ln_rstd, fmaf(-ln_rm, cc.y, dd.y));
+              f[4 * j4 + 2] = fmaf(f[4 * j4 + 2], ln_rstd, fmaf(-ln_rm, cc.z, dd.z));
+              f[4 * j4 + 3] = fmaf(f[4 * j4 + 3], ln_rstd, fmaf(-ln_rm, cc.w, dd.w));
+            }
+          }
           if (staged && sub == 0) {  // this slab's residual / lora_up rows have landed (the next slab's copy may be in flight)
             if (kEpiBufs == 2 && more)
               cp_async_wait<1>();
@@ -624,6 +683,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             float gb[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) gb[j] = __uint_as_float(g[j]);
+            if (p.ln_stats != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                gb[j] = fmaf(gb[j], ln_rstd, fmaf(-ln_rm, __ldg(p.ln_c + p.Nout + n + j), __ldg(p.ln_d + p.Nout + n + j)));
+            }
             if (p.flags & SB200_EPI_BIAS) add_bf16x16(gb, p.bias + p.Nout + n);
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_f(gb[j]);
@@ -640,6 +704,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = add_bf16x2(o[j], rw[j]);
+          }
+          if (p.rs_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float lo = bf16_lo(o[j]), hi = bf16_hi(o[j]);
+              rs1 += lo + hi;
+              rs2 = fmaf(lo, lo, fmaf(hi, hi, rs2));
+            }
           }
           st_shared_v4(a0, make_uint4(o[0], o[1], o[2], o[3]));
           st_shared_v4(a1, make_uint4(o[4], o[5], o[6], o[7]));
@@ -683,6 +755,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
             mbar_arrive_cluster(tempty_leader + 8u * as);
           else
             mbar_arrive(bar_tempty + 8u * as);
+        }
+      }
+      if (p.rs_out != nullptr) {
+        // The kEpiPerQuarter warps of a lane quarter hold partial sums of the SAME 32 rows (different slabs): combine
+        // them through the quarter's first warp's staging buffer (free between its last copy-out and its next
+        // prefetch), so that a row has one slot per N tile.  Named barrier 1 + q, 32 * kEpiPerQuarter threads.
+        const uint32_t red = tiles + static_cast<uint32_t>(S) * stage_bytes +
+                             static_cast<uint32_t>(q) * (kEpiBytesPerWarp + kEpiBufs * p.up_buf_bytes);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kEpiPerQuarter) : "memory");  // first warp done with its buffer
+        if (hsel != 0)
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + ((hsel - 1) * 32 + lane) * 8), "f"(rs1), "f"(rs2)
+                       : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kEpiPerQuarter) : "memory");
+        if (hsel == 0) {
+#pragma unroll
+          for (int w = 0; w < kEpiPerQuarter - 1; ++w) {
+            float a, b;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (w * 32 + lane) * 8));
+            rs1 += a;
+            rs2 += b;
+          }
+          if (row_ok)
+            reinterpret_cast<float2*>(p.rs_out)[static_cast<size_t>(nt) * p.M + my_row] = make_float2(rs1, rs2);
         }
       }
       as ^= 1;
@@ -883,6 +978,15 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
                           int K0, const void* w, int ldw, void* out, int ldo, int M, int N, int K,
                           int flags, const void* bias, const void* rowbias, int rows_per_batch,
                           const void* resid, int ldr, const sb200_lora* lora, int bn_arg) {
+  return sb200_gemm_ln(handle, stream, x0, ldx0, x1, ldx1, K0, w, ldw, out, ldo, M, N, K, flags, bias, rowbias,
+                       rows_per_batch, resid, ldr, lora, bn_arg, nullptr, nullptr, 0, nullptr);
+}
+
+extern "C" int sb200_gemm_ln(void* handle, void* stream, const void* x0, int ldx0, const void* x1, int ldx1,
+                             int K0, const void* w, int ldw, void* out, int ldo, int M, int N, int K,
+                             int flags, const void* bias, const void* rowbias, int rows_per_batch,
+                             const void* resid, int ldr, const sb200_lora* lora, int bn_arg,
+                             const sb200_lnfold* ln, float* rowstats, int rowstats_cap, int* rowstats_parts) {
   Ctx* ctx = as_ctx(handle);
   SB200_REQUIRE(ctx, "gemm: NULL handle");
   SB200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad dims M=%d N=%d K=%d", M, N, K);
@@ -942,6 +1046,26 @@ extern "C" int sb200_gemm(void* handle, void* stream, const void* x0, int ldx0, 
   p.ldr = ldr;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
+  if (ln != nullptr) {
+    SB200_REQUIRE(ln->stats && ln->parts > 0 && ln->C == K && ln->c && ln->d, "gemm: lnfold arguments (C must equal K)");
+    SB200_REQUIRE(!(flags & SB200_EPI_BIAS), "gemm: with lnfold the bias lives in d[]");
+    SB200_REQUIRE(!has_lora || (ln->c_lora && ln->d_lora), "gemm: lnfold with LoRA needs c_lora / d_lora");
+    p.ln_stats = ln->stats;
+    p.ln_parts = ln->parts;
+    p.ln_inv_c = 1.0f / static_cast<float>(ln->C);
+    p.ln_eps = ln->eps;
+    p.ln_c = ln->c;
+    p.ln_d = ln->d;
+    p.ln_cl = has_lora ? ln->c_lora : nullptr;
+    p.ln_dl = has_lora ? ln->d_lora : nullptr;
+  }
+  if (rowstats != nullptr) {
+    SB200_REQUIRE(!geglu, "gemm: rowstats of a GEGLU output are not supported");
+    p.rs_parts = p.num_n_tiles;
+    SB200_REQUIRE(p.rs_parts <= rowstats_cap, "gemm: rowstats needs %d slots per row, capacity %d", p.rs_parts, rowstats_cap);
+    p.rs_out = rowstats;
+    if (rowstats_parts) *rowstats_parts = p.rs_parts;
+  }
 
   int st;
   {

@@ -278,7 +278,12 @@ def test_full_sdxl_parity_vs_fp32_oracle(dev, batch):
     with torch.no_grad():
         got = pm(x, 500, ehs, added_cond_kwargs=added).sample
         ref = om(x.float(), 500, ehs.float(), added_cond_kwargs=addf).sample
-    assert rel_rms(got, ref) < 2.5e-2
+    # SURVEY.md §4 bar for the full-size model: rel-RMS <= 1e-2, max-abs <= 3e-2 (bf16 product vs fp32 oracle; the
+    # reference itself runs this path in fp16/bf16 autocast, so the oracle is the tighter of the two comparisons)
+    print(f"full SDXL base: rel_rms {rel_rms(got, ref):.4g} max_abs {(got.float() - ref).abs().max().item():.4g} "
+          f"ref_rms {ref.pow(2).mean().sqrt().item():.4g}")
+    assert rel_rms(got, ref) < 1e-2
+    assert (got.float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
     with c3lier(plora):
         net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
     assert len(net.unet_loras) == 346
@@ -294,8 +299,17 @@ def test_full_sdxl_parity_vs_fp32_oracle(dev, batch):
         net.set_lora_slider(2.0)
         with net:
             got_l = pm(x, 19, ehs, added_cond_kwargs=added).sample
-    assert rel_rms(got_l, ref_l) < 2.5e-2
-    assert (got_l.float() - ref_l).abs().max().item() < 0.15
+    print(f"full SDXL + LoRA(346, slider 2): rel_rms {rel_rms(got_l, ref_l):.4g} "
+          f"max_abs {(got_l.float() - ref_l).abs().max().item():.4g} ref_max {ref_l.abs().max().item():.4g}")
+    assert rel_rms(got_l, ref_l) < 1e-2
+    assert (got_l.float() - ref_l).abs().max().item() < 3e-2 * max(1.0, ref_l.abs().max().item())
+    # the same forward with LayerNorm folded into the consuming projections (sb200_gemm_ln; off by default)
+    pm.fuse_layernorm = True
+    with torch.no_grad(), net:
+        got_f = pm(x, 19, ehs, added_cond_kwargs=added).sample
+    pm.fuse_layernorm = False
+    print(f"  LayerNorm-folded: rel_rms {rel_rms(got_f, ref_l):.4g}")
+    assert rel_rms(got_f, ref_l) < 1e-2
 
 
 def test_denoise_loop_with_slider_gating(dev):
