@@ -256,6 +256,10 @@ int sb200_cfg_ddim(void* handle, void* stream, const void* eps2, int eps_is_f32,
 int sb200_cfg_step(void* handle, void* stream, const void* eps2, int eps_is_f32, float g, const void* x, float cx,
                    float ce, void* x_prev, void* eps_out, int out_is_f32, int64_t n);
 
+/* Debug: clock64 phase stamps of CTA (0,0,0) of the last ping-pong attention launch made with SB200_ATTN_POLY=1
+ * (layout: sliders_b200/csrc/attention.cu, g_pp_trace).  n <= 8192 values.  Synchronises the device. */
+int sb200_debug_attention_trace(long long* dst, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,6 +158,9 @@ def test_conv3x3(dev, force, B, H, W, C0, C1, Cout, stride, flags, lora):
     (1, 2, 64, 64, True),      # Sq, Skv below one tile
     (1, 3, 320, 200, False),   # ragged queries and keys
     (1, 10, 4096, 4096, True),  # SDXL 64x64 level
+    (1, 3, 700, 600, False),   # ping-pong kernel (two query tiles per CTA): ragged last CTA, partial last key tile
+    (2, 2, 300, 520, False),   # second query tile of the last CTA entirely out of range
+    (1, 2, 1024, 513, False),  # one key in the last tile
 ])
 def test_attention(dev, B, heads, Sq, Skv, fused):
     from sliders_b200 import ops
@@ -191,6 +194,31 @@ def test_attention_softmax_rows_sum_to_one(dev):
     v = torch.ones(B * S, heads * 64, device=dev, dtype=BF)
     out = ops.attention(q, k, v, B, heads, S, S, 0.125)
     assert (out.float() - 1).abs().max().item() < 2e-2
+
+
+def test_attention_growing_logits_rescale(dev):
+    """Keys ordered so the row maximum keeps growing tile after tile (by much more than the 2^8 lazy-rescale
+    threshold): every key tile triggers the accumulator rescale, in both forward kernels, and the log-sum-exp the
+    backward pass consumes matches."""
+    from sliders_b200 import ops
+
+    B, heads, S = 1, 2, 1024
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(B * S, heads * 64, generator=g).abs()
+    k = torch.randn(B * S, heads * 64, generator=g).abs() * torch.linspace(0.2, 6.0, S).repeat(B)[:, None]
+    v = torch.randn(B * S, heads * 64, generator=g)
+    q, k, v = q.to(dev, BF), k.to(dev, BF), v.to(dev, BF)
+    lse = torch.empty(B, heads, S, device=dev, dtype=torch.float32)
+    out = ops.attention(q, k, v, B, heads, S, S, 0.125, lse=lse)
+    qf = q.float().reshape(B, S, heads, 64).transpose(1, 2)
+    kf = k.float().reshape(B, S, heads, 64).transpose(1, 2)
+    vf = v.float().reshape(B, S, heads, 64).transpose(1, 2)
+    sc = qf @ kf.transpose(-1, -2) * 0.125
+    assert (sc.amax(-1)[..., None] - sc[..., :128].amax(-1)[..., None]).min().item() > 16   # the max really grows
+    ref = (torch.softmax(sc, dim=-1) @ vf).transpose(1, 2).reshape(B * S, heads * 64)
+    assert rel_rms(out, ref) < 2e-2
+    ref_lse = torch.logsumexp(sc, dim=-1) * 1.4426950408889634
+    assert (lse - ref_lse).abs().max().item() < 5e-2
 
 
 @pytest.mark.parametrize("B,HW,C0,C1,silu,eps", [(2, 1024, 320, 0, True, 1e-5), (2, 4096, 640, 320, True, 1e-5),
