@@ -483,9 +483,11 @@ def main():
     train = None
     if not args.no_train:
         net.requires_grad_(True)
-        parallel.broadcast_lora_params(net)
+        # more than 4 GPUs: independent sliders side by side, 4 ranks each (the iteration does not shard further)
+        sgroup, sidx, n_sliders = parallel.slider_groups(4) if world > 4 else (None, 0, 1)
+        parallel.broadcast_lora_params(net, sgroup)
         opt = train_util.get_optimizer("AdamW")(net.prepare_optimizer_params(), lr=2e-4)
-        gtr = torch.Generator().manual_seed(77)
+        gtr = torch.Generator().manual_seed(77 + sidx)
         mk = lambda: trainer.PromptEmbedsXL(torch.randn(1, 77, 2048, generator=gtr).to(dev, torch.bfloat16),
                                             torch.randn(1, 1280, generator=gtr).to(dev, torch.bfloat16))
         unc, tgt, pos = mk(), mk(), mk()
@@ -497,23 +499,27 @@ def main():
 
         def text_it():
             state["loss"] = trainer.text_slider_step_xl(unet, net, tsched, opt, None, pair, timesteps_to=25, device=dev,
-                                                        weight_dtype=torch.bfloat16,
+                                                        weight_dtype=torch.bfloat16, group=sgroup,
                                                         generator=torch.Generator().manual_seed(1000 + state["it"]))
             state["it"] += 1
 
         n_it = 3
         it_ms = timed(text_it, n_it, 1, dm)
-        parallel.assert_replicas_equal(list(net.parameters()))
+        parallel.assert_replicas_equal(list(net.parameters()), sgroup)
         passes = 2 * (25 + 4)  # CFG pairs: 25 denoise steps + positive / neutral / unconditional / target
+        gw = world // n_sliders  # ranks per slider
         train = {"what": "BASELINE config 3 — text-slider iteration, SDXL 1024 px, batch 1, rank-4 LoRA "
                          "(train_lora_xl.py:162-356): 25 DDIM denoise steps (guidance 3) + 4 CFG-pair predictions + "
                          "backward-to-LoRA + AdamW(692 tensors)",
                  "ms_per_iteration": it_ms, "iterations_timed": n_it, "passes_per_iteration": passes,
-                 "passes_per_s": passes / (it_ms * 1e-3), "loss": float(state["loss"]),
+                 "sliders_in_parallel": n_sliders, "ranks_per_slider": gw,
+                 "iterations_per_s": n_sliders / (it_ms * 1e-3),
+                 "passes_per_s": n_sliders * passes / (it_ms * 1e-3), "loss": float(state["loss"]),
                  "replicas_equal_after": True,
                  "sharding": ("single GPU" if world == 1 else
+                              (f"{n_sliders} independent sliders x {gw} ranks; within a slider: " if n_sliders > 1 else "") +
                               f"denoise CFG-split over rank parity (1 all-gather of 64 KiB per step), target prediction on rank "
-                              f"{world - 1}, frozen predictions over ranks 0..{max(world - 2, 0)}, 1 LoRA-grad all-reduce")}
+                              f"{gw - 1}, frozen predictions over ranks 0..{max(gw - 2, 0)}, 1 LoRA-grad all-reduce")}
         net.requires_grad_(False)
         opt = None
         unet.reset_graphs() if hasattr(unet, "reset_graphs") else None

@@ -140,3 +140,26 @@ def assert_replicas_equal(params: Sequence[torch.Tensor], group: Optional[dist.P
     if not torch.equal(lo, hi):
         raise RuntimeError(f"{what} differ between ranks (checksum min {lo.tolist()} max {hi.tolist()}): broadcast them "
                            "once at setup (parallel.broadcast_lora_params)")
+
+
+def slider_groups(ranks_per_slider: int = 4):
+    """Splits the job into independent slider groups of `ranks_per_slider` consecutive ranks and returns
+    (this rank's group, its index, number of groups).  One text-slider iteration is a serial chain of batch-1 forwards
+    whose sharding stops paying at 4 ranks (CFG halves x {target, frozen predictions}), so a node with
+    more GPUs trains several sliders (attributes / prompt files) side by side, each exactly as a 4-rank job would.
+    Every rank must call this (dist.new_group is collective).  Without torch.distributed: (None, 0, 1)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return None, 0, 1
+    world, rank = dist.get_world_size(), dist.get_rank()
+    size = max(1, min(int(ranks_per_slider), world))
+    if world % size != 0:
+        raise ValueError(f"world size {world} is not a multiple of ranks_per_slider={size}")
+    n = world // size
+    if n == 1:
+        return None, 0, 1
+    mine = None
+    for g in range(n):
+        grp = dist.new_group(list(range(g * size, (g + 1) * size)))
+        if rank // size == g:
+            mine = grp
+    return mine, rank // size, n

@@ -209,6 +209,43 @@ def test_fanout_two_ranks_gloo(tmp_path):
         assert p.returncode == 0 and "ok" in o, o
 
 
+_GROUPS_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sliders_b200 import parallel
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=4)
+rank = dist.get_rank()
+grp, idx, n = parallel.slider_groups(2)
+assert n == 2 and idx == rank // 2 and dist.get_world_size(grp) == 2
+# each group is its own job: draws follow the group's rank 0, gradients are summed inside the group only
+vals = parallel.sync_draws([float(rank), 7.0], "cpu", grp)
+assert vals == [float(2 * idx), 7.0], vals
+p = torch.nn.Parameter(torch.zeros(3)); p.grad = torch.full((3,), float(rank + 1))
+parallel.allreduce_lora_grads([p], group=grp)
+assert torch.equal(p.grad, torch.full((3,), float(4 * idx + 3))), p.grad    # (1+2) or (3+4)
+net = torch.nn.Linear(2, 2); torch.nn.init.constant_(net.weight, float(rank)); torch.nn.init.zeros_(net.bias)
+parallel.broadcast_lora_params(net, grp)
+assert torch.equal(net.weight, torch.full((2, 2), float(2 * idx)))
+parallel.assert_replicas_equal(list(net.parameters()), grp)
+g1, i1, n1 = parallel.slider_groups(4)
+assert g1 is None and (i1, n1) == (0, 1)
+dist.destroy_process_group()
+print("ok")
+'''
+
+
+def test_slider_groups_four_ranks_gloo(tmp_path):
+    """More GPUs than one iteration can use: independent sliders side by side, each group a closed job."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GROUPS_WORKER)
+    port = 31500 + (os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(4)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o
+
+
 def test_launch_plan_dry_run_counts_and_flops():
     """Dry-run the SDXL forward on the meta device with shape-recording stand-ins for the kernels: the launch plan
     must contain every Linear/conv FLOP of SURVEY.md §8d (6.761 TFLOP per pass incl. attention) and the fusions
