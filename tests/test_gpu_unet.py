@@ -283,7 +283,7 @@ def test_full_sdxl_parity_vs_fp32_oracle(dev, batch):
     print(f"full SDXL base: rel_rms {rel_rms(got, ref):.4g} max_abs {(got.float() - ref).abs().max().item():.4g} "
           f"ref_rms {ref.pow(2).mean().sqrt().item():.4g}")
     assert rel_rms(got, ref) < 1e-2
-    assert (got.float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    assert (got.float() - ref).abs().max().item() < 3e-2          # measured 0.0221 (deterministic kernels, fixed seeds)
     with c3lier(plora):
         net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
     assert len(net.unet_loras) == 346
@@ -302,7 +302,7 @@ def test_full_sdxl_parity_vs_fp32_oracle(dev, batch):
     print(f"full SDXL + LoRA(346, slider 2): rel_rms {rel_rms(got_l, ref_l):.4g} "
           f"max_abs {(got_l.float() - ref_l).abs().max().item():.4g} ref_max {ref_l.abs().max().item():.4g}")
     assert rel_rms(got_l, ref_l) < 1e-2
-    assert (got_l.float() - ref_l).abs().max().item() < 3e-2 * max(1.0, ref_l.abs().max().item())
+    assert (got_l.float() - ref_l).abs().max().item() < 3e-2      # measured 0.0234
     # the same forward with LayerNorm folded into the consuming projections (sb200_gemm_ln; off by default)
     pm.fuse_layernorm = True
     with torch.no_grad(), net:
@@ -548,6 +548,57 @@ def test_tiny_xl_gradients_other_train_methods(dev, method, n_expected):
     assert (num / den) ** 0.5 < 5e-2, (method, (num / den) ** 0.5)
     if method != "selfattn":
         assert any("attn2_to_k" in l.lora_name for l in net.unet_loras)
+
+
+@pytest.mark.parametrize("h,w", [(72, 88), (40, 104), (24, 36)])
+def test_tiny_xl_bucket_resolutions_forward_and_gradients(dev, h, w):
+    """`dynamic_resolution` draws latent sizes that are multiples of 8 but neither square nor powers of two
+    (train_util.get_random_resolution_in_bucket: 64..120 for the 1024 bucket), and eval runs at e.g. 768x512: the
+    3x3 convolutions tile such images in <= 128-pixel patches with TMA zero fill, the token counts (h*w, h*w/4, ...)
+    are ragged for the attention tiles.  Forward and LoRA gradients against the fp32 oracle."""
+    from oracle import unet as ounet
+    from sliders_b200 import lora as plora, synthetic
+    from sliders_b200.unet import UNet2DConditionModel, UNetConfig
+
+    ocfg = ounet.UNetConfig.tiny_xl()
+    pm = UNet2DConditionModel(UNetConfig.from_dict(ocfg.__dict__))
+    synthetic.init_synthetic_(pm, seed=31)
+    om = ounet.UNet2DConditionModel(ocfg)
+    pm = pm.to(dev, BF).eval().requires_grad_(False)
+    om.load_state_dict({k: v.float() for k, v in pm.state_dict().items()})  # the bf16-rounded weights
+    om = om.to(dev).eval().requires_grad_(False)
+    with c3lier(plora):
+        net = plora.LoRANetwork(pm, rank=4, multiplier=1.0, alpha=1.0, train_method="noxattn").to(dev, BF)
+    synthetic.init_lora_nonzero_(net, seed=32, up_std=0.05, reseed_down=True)
+    net.requires_grad_(True)
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    x = torch.randn(2, 4, h, w, generator=g).to(dev, BF)
+    ehs = torch.randn(2, 77, ocfg.cross_attention_dim, generator=g).to(dev, BF)
+    added = {"text_embeds": torch.randn(2, 128, generator=g).to(dev, BF),
+             "time_ids": torch.tensor([[8. * h, 8. * w, 0., 0., 8. * h, 8. * w]] * 2, device=dev)}
+    goal = torch.randn(2, 4, h, w, generator=g).to(dev)
+    net.set_lora_slider(1.0)
+    with net:
+        pred = pm(x, 321, encoder_hidden_states=ehs, added_cond_kwargs=added).sample
+    assert pred.shape == (2, 4, h, w) and pred.requires_grad
+    torch.nn.functional.mse_loss(pred.float(), goal).backward()
+    torch.cuda.synchronize()
+
+    def call(fp):
+        out = torch.func.functional_call(om, fp, (x.float(), 321, ehs.float()),
+                                         {"added_cond_kwargs": {k: v.float() for k, v in added.items()}}).sample
+        assert rel_rms(pred, out) < 3e-2
+        return torch.nn.functional.mse_loss(out, goal)
+
+    leaves = _oracle_lora_grads(om, net, 1.0, call)
+    num = den = 0.0
+    for l in net.unet_loras:
+        for got, ref in ((l.lora_down.weight.grad, leaves[l.lora_name][0].grad),
+                         (l.lora_up.weight.grad, leaves[l.lora_name][1].grad)):
+            assert got is not None and torch.isfinite(got).all(), l.lora_name
+            num += (got.float() - ref).pow(2).sum().item()
+            den += ref.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 5e-2, ((h, w), (num / den) ** 0.5)
 
 
 def test_full_size_inference_sweep_properties(dev):
