@@ -232,7 +232,7 @@ def class_timings(unet, call, steps, warmup):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU legs
-def cpu_pair_call(arch="sdxl", rank=4, seed=0, lora_state=None):
+def cpu_pair_call(arch="sdxl", rank=4, seed=0, lora_state=None, unet_state=None):
     """The reference's CPU path for one CFG-pair call of the headline workload: `predict_noise_xl` with the LoRA hook
     live on the fp32 oracle UNet.  Returns (callable -> eps, kind, description)."""
     from oracle import reference_bridge as rb
@@ -244,8 +244,12 @@ def cpu_pair_call(arch="sdxl", rank=4, seed=0, lora_state=None):
     with torch.device("meta"):
         om = ounet.UNet2DConditionModel(cfg)
     om = om.to_empty(device="cpu")
-    om.load_state_dict({k: synthetic.synthetic_tensor(k, p.shape, seed + 1, "cpu") for k, p in om.named_parameters()},
-                       assign=True)
+    if unet_state is not None:   # the kernel path's own (bf16) weights: the device generator draws a different stream
+        om.load_state_dict({k: unet_state[k].detach().to("cpu", torch.float32).contiguous() for k, _ in om.named_parameters()},
+                           assign=True)
+    else:
+        om.load_state_dict({k: synthetic.synthetic_tensor(k, p.shape, seed + 1, "cpu")
+                            for k, p in om.named_parameters()}, assign=True)
     om.requires_grad_(False)
     om.eval()
     if rb.available():
@@ -575,7 +579,8 @@ def main():
         threads = host_threads()
         torch.set_num_threads(threads)
         t0 = time.time()
-        call, kind, what, (lat1, ehs2, pooled2, tids2) = cpu_pair_call("sdxl", lora_state=net.state_dict())
+        call, kind, what, (lat1, ehs2, pooled2, tids2) = cpu_pair_call("sdxl", lora_state=net.state_dict(),
+                                                                        unet_state=unet.state_dict())
         eps_cpu = call()                      # warm-up
         times = []
         while not times or (time.time() - t0 < args.cpu_seconds and len(times) < 3):
