@@ -147,6 +147,7 @@ struct AttnParams {
   int d;           // head dim (multiple of 8)
   int n_kv_tiles;
   int split_issue;   // 1: Q K^T issued by the TMA warp, P V by the MMA warp (default); 0: both by the MMA warp
+  int split_exp;     // two-CTA kernel: 1 = issue a chunk's 32 exponentials, fence, then sum / pack them
   int pp_token;      // ping-pong kernel: 1 = the two warpgroups hand the MUFU unit to each other explicitly
   float scale_log2;  // scale * log2(e)
 };
@@ -393,7 +394,14 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
         uint32_t pk[16];
         if (kv_left >= (c + 1) * 32) {  // warp-uniform: no masking code on full chunks
           uint64_t acc[2] = {0ull, 0ull};
-          exp_chunk32<kPoly>(v, p.scale_log2, m_run, pk, acc);
+          if (p.split_exp) {
+            // all 32 exponentials in flight before the first one is read (see exp_issue32)
+            exp_issue32<kPoly>(v, p.scale_log2, m_run);
+            __syncwarp();
+            exp_consume32(v, pk, acc);
+          } else {
+            exp_chunk32<kPoly>(v, p.scale_log2, m_run, pk, acc);
+          }
           float a0, a1, a2, a3;
           f2_unpack(acc[0], a0, a1);
           f2_unpack(acc[1], a2, a3);
@@ -906,6 +914,11 @@ extern "C" int sb200_attention(void* handle, void* stream, const void* q, int ld
       return e && e[0] == '1';
     }();
     p.pp_token = token ? 1 : 0;
+    static const bool split_exp = [] {
+      const char* e = getenv("SB200_ATTN_SPLIT_EXP");
+      return e && e[0] == '1';
+    }();
+    p.split_exp = split_exp ? 1 : 0;
   }
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
