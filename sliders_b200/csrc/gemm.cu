@@ -94,6 +94,8 @@ struct GemmParams {
   int bw, bh, bb;   // conv patch of one sub-tile (bw * bh * bb <= 128 pixels)
   int tiles_w, tiles_h;
   int flags;
+  int quad;         // CTA pairs launched as 2x2 clusters: two pairs on the same rows, A tile multicast to both (tmA[2..3]
+                    // = half-height boxes); consecutive N tiles go to the two pairs of a cluster
   int mma_unroll2;  // issue two k-blocks per elect region (SB200_MMA_UNROLL, default 1)
   int debug;        // profiling experiments only: bit 0 skip W loads, bit 1 skip A loads, bit 3 skip the epilogue (garbage)
   const __nv_bfloat16* bias;
@@ -194,7 +196,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const uint32_t crank = kCtas == 2 ? cluster_ctarank() : 0u;   // rank in the cluster (0..1, or 0..3 in quad mode)
+  const uint32_t cta_rank = crank & 1u;                          // rank inside the CTA pair
+  const uint32_t pair_id = crank >> 1;                           // which pair of a 2x2 cluster
+  const uint32_t lead = crank & ~1u;                             // cluster rank of this pair's leader
+  const bool quad = kCtas == 2 && p.quad != 0;
   const bool leader = cta_rank == 0;
   const int S = p.stages;
   const uint32_t bar_full = base;                 // S barriers (used in the leader CTA)
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(bar_full + 8u * i, 1);
-      mbar_init(bar_empty + 8u * i, 1);
+      mbar_init(bar_empty + 8u * i, quad ? 2 : 1);  // quad: the stage is overwritten from both pairs, both must be done
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8u * i, 1);
@@ -241,10 +247,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int unit = blockIdx.x / kCtas;          // persistent work unit (CTA or CTA pair)
-  const int num_units = gridDim.x / kCtas;
-  const int num_n_tiles = p.num_n_tiles, num_m_tiles = p.num_m_tiles, n_fast = p.n_fast;
+  // persistent work unit: CTA, CTA pair, or (quad) a cluster of two pairs that walks PAIRS of adjacent N tiles
+  const int ctas_per_unit = quad ? 4 : kCtas;
+  const int unit = blockIdx.x / ctas_per_unit;
+  const int num_units = gridDim.x / ctas_per_unit;
+  const int num_n_tiles = quad ? p.num_n_tiles / 2 : p.num_n_tiles, num_m_tiles = p.num_m_tiles, n_fast = p.n_fast;
+  const int total_tiles = num_m_tiles * num_n_tiles;
+  const int nt_mul = quad ? 2 : 1, nt_add = quad ? static_cast<int>(pair_id) : 0;
   const int kblocks = p.kblocks;
   const uint32_t stage_bytes = static_cast<uint32_t>(p.stage_bytes);
   const uint32_t a_bytes = kBM * 128;
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       if (t != cur_t) {              // tile coordinates (once per tile and warp)
         cur_t = t;
         const int mt = n_fast ? t / num_n_tiles : t % num_m_tiles;
-        nt = n_fast ? t % num_n_tiles : t / num_m_tiles;
+        nt = (n_fast ? t % num_n_tiles : t / num_m_tiles) * nt_mul + nt_add;
         const int st = mt * kCtas + static_cast<int>(cta_rank);  // this CTA's 128-row sub-tile
         m0 = st * kBM;
         b0 = h0 = w0 = 0;
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           // bytes of the pair).  The peer's bytes for this stage cannot land before the previous use of the
           // stage completed (its empty barrier is released by the leader's commit after that phase), and a
           // transiently negative tx-count inside the right phase is legal.
-          full = mapa_u32(full, 0);
+          full = mapa_u32(full, lead);
           if (leader) mbar_expect_tx(full_bar, 2u * tx);
         } else {
           mbar_expect_tx(full, tx);
@@ -348,10 +357,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         }
         if constexpr (kCtas == 2) {
           if (!skip_a) {
-            if (a_mode == 0)
+            if (quad) {
+              // the CTAs with this pair rank in both pairs need the same 128 rows: each loads 64 of them and multicasts
+              // to both (L2 -> SM traffic of A halves; the N = 1280 shapes are bound by it)
+              const int src = kb < kb_split ? 0 : 1;
+              tma_load_2d_2cta_mc(sA + pair_id * (a_bytes >> 1), &p.tmA[2 + src], full_bar & 0xFEFFFFFFu, c0,
+                                  c1 + static_cast<int>(pair_id) * (kBM / 2),
+                                  static_cast<uint16_t>((1u << cta_rank) | (4u << cta_rank)));
+            } else if (a_mode == 0) {
               tma_load_2d_2cta(sA, amap, full, c0, c1);
-            else
+            } else {
               tma_load_4d_2cta(sA, amap, full, c0, c1, c2, c3);
+            }
           }
           if (!skip_w) tma_load_2d_2cta(sB, &p.tmB, full, kb * kBK, brow);
           if (has_lora) tma_load_2d_2cta(sB + b_bytes, &p.tmL, full, kb * kBK, static_cast<int>(cta_rank) * p.l_rows);
@@ -391,6 +408,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     // ------------------------------------------------------------------ MMA issuer (leader CTA only), converged warp
     if (leader) {
       const uint32_t idesc = umma_idesc_bf16(kBM * kCtas, bn + rt);
+      const uint16_t pair_mask = static_cast<uint16_t>(3u << (2u * pair_id));    // this pair's two CTAs
+      const uint16_t empty_mask = quad ? static_cast<uint16_t>(0xF) : pair_mask;  // who refills this pair's stages
       // The loop below is the issue-side critical path (one pass per 64-deep k-block has to fit inside the 4 UMMAs'
       // tensor time: 2 (bn + rt) cycles), so everything it needs is a running register value: descriptor low words and
       // barrier addresses advance by constants and wrap with the stage counter, nothing is recomputed from the stage
@@ -424,7 +443,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         }
         // free the smem stage (in every CTA of the pair) once these MMAs retire
         if constexpr (kCtas == 2)
-          umma_commit_2cta(ebar, 3);
+          umma_commit_2cta(ebar, empty_mask);
         else
           umma_commit(ebar);
       };
@@ -476,7 +495,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         }
         if (elect_one()) {  // accumulator complete once everything issued so far retires
           if constexpr (kCtas == 2)
-            umma_commit_2cta(bar_tfull + 8u * as, 3);
+            umma_commit_2cta(bar_tfull + 8u * as, pair_mask);
           else
             umma_commit(bar_tfull + 8u * as);
         }
@@ -501,7 +520,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
         has_lora ? (p.lora_scale_dev ? p.lora_scale * __ldg(p.lora_scale_dev) : p.lora_scale) : 0.f;
     const bool has_resid = (p.flags & SB200_EPI_RESID) != 0;
     const bool skip_epi = (p.debug & 8) != 0;
-    const uint32_t tempty_leader = kCtas == 2 ? mapa_u32(bar_tempty, 0) : bar_tempty;
+    const uint32_t tempty_leader = kCtas == 2 ? mapa_u32(bar_tempty, lead) : bar_tempty;
     // accumulator column of output column c / of LoRA-down row j (see the header: the pair interleaves its halves)
     const int half_cols = bn >> 1, lr_half = rt >> 1;
     const bool pair_lora = kCtas == 2 && has_lora;
@@ -516,7 +535,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     const long long st_t0 = kStats ? clock64() : 0;
     for (int t = unit; t < total_tiles; t += num_units) {
       const int mt = n_fast ? t / num_n_tiles : t % num_m_tiles;
-      const int nt = n_fast ? t % num_n_tiles : t / num_m_tiles;
+      const int nt = (n_fast ? t % num_n_tiles : t / num_m_tiles) * nt_mul + nt_add;
       const int st = mt * kCtas + static_cast<int>(cta_rank);
       // output row of this thread's accumulator row (q * 32 + lane), or -1 (padding row of the tile)
       int my_row = -1, my_batch = 0;
@@ -919,8 +938,36 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
     else
       SB200_CUDA_CHECK(launch_pdl(gemm_kernel<1>, dim3(grid), dim3(kGemmThreads), smem, stream, p));
   } else {
-    const int units = ctx->num_sms / 2;
-    const int grid = 2 * (total < units ? total : units);
+    const int csize = p.quad ? 4 : 2;
+    int units = ctx->num_sms / csize;
+    int work = total;
+    if (p.quad) {
+      // clusters of four must fit inside a GPC: ask the driver how many are resident at once (once per context)
+      static int quad_clusters = 0;
+      if (quad_clusters == 0) {
+        cudaLaunchConfig_t qc;
+        memset(&qc, 0, sizeof(qc));
+        qc.gridDim = dim3(4 * (ctx->num_sms / 4));
+        qc.blockDim = dim3(kGemmThreads);
+        qc.dynamicSmemBytes = kSmemBudget;
+        cudaLaunchAttribute qa;
+        qa.id = cudaLaunchAttributeClusterDimension;
+        qa.val.clusterDim.x = 4;
+        qa.val.clusterDim.y = 1;
+        qa.val.clusterDim.z = 1;
+        qc.attrs = &qa;
+        qc.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<2>, &qc) != cudaSuccess || n <= 0) {
+          cudaGetLastError();
+          n = ctx->num_sms / 4;
+        }
+        quad_clusters = n < ctx->num_sms / 4 ? n : ctx->num_sms / 4;
+      }
+      units = quad_clusters;
+      work = p.num_m_tiles * (p.num_n_tiles / 2);
+    }
+    const int grid = csize * (work < units ? work : units);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -929,7 +976,7 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
     cfg.stream = stream;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.x = csize;
     attr.val.clusterDim.y = 1;
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
@@ -1092,6 +1139,26 @@ extern "C" int sb200_gemm_ln(void* handle, void* stream, const void* x0, int ldx
     const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
     const uint32_t box[2] = {kBK, static_cast<uint32_t>(lora->rt / tc.ctas)};
     if ((st = make_tmap_bf16(ctx, &p.tmL, lora->down, 2, dims, strides, box))) return st;
+  }
+  // 2x2 clusters with the A tile multicast to both pairs: for shapes that stream more bytes from L2 than the tensor
+  // pipe can cover (narrow tiles: the N = 1280 projections).  SB200_QUAD: 0 off, 1 = tiles up to 192 wide, 2 = always.
+  {
+    static const int quad_env = env_int("SB200_QUAD", 0);
+    const bool want = quad_env >= 2 || (quad_env == 1 && tc.bn + (has_lora ? lora->rt : 0) <= 208);
+    if (want && tc.ctas == 2 && !geglu && p.num_n_tiles % 2 == 0 && p.num_n_tiles >= 2) {
+      p.quad = 1;
+      const uint32_t hbox[2] = {kBK, kBM / 2};
+      {
+        const uint64_t dims[2] = {static_cast<uint64_t>(K0), static_cast<uint64_t>(M)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(ldx0) * 2};
+        if ((st = make_tmap_bf16(ctx, &p.tmA[2], x0, 2, dims, strides, hbox))) return st;
+      }
+      if (split) {
+        const uint64_t dims[2] = {static_cast<uint64_t>(K - K0), static_cast<uint64_t>(M)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(ldx1) * 2};
+        if ((st = make_tmap_bf16(ctx, &p.tmA[3], x1, 2, dims, strides, hbox))) return st;
+      }
+    }
   }
   return launch_gemm(ctx, static_cast<cudaStream_t>(stream), p, tc.ctas);
 }

@@ -285,6 +285,18 @@ __device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap
       : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same load multicast to the CTAs in `cta_mask`: the box lands at offset `dst` in each of them and each
+// destination's transaction bytes are signalled at the barrier offset / peer bit given by `bar` inside the DESTINATION's
+// own CTA pair (so `bar` = this CTA's barrier address with the peer bit cleared = "the leader of the pair").
+__device__ __forceinline__ void tma_load_2d_2cta_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar,
                                                  int c0, int c1, int c2, int c3) {
   asm volatile(
