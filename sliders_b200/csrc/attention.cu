@@ -147,6 +147,8 @@ struct AttnParams {
   int d;           // head dim (multiple of 8)
   int n_kv_tiles;
   int split_issue;   // 1: Q K^T issued by the TMA warp, P V by the MMA warp (default); 0: both by the MMA warp
+  int q_per_cta;     // two-CTA kernel: consecutive 128-query tiles one CTA walks (> 1 for short key sequences: the
+                     // per-CTA fixed cost of a cross-attention tile is several times its work)
   int split_exp;     // two-CTA kernel: 1 = issue a chunk's 32 exponentials, fence, then sum / pack them
   int pp_token;      // ping-pong kernel: 1 = the two warpgroups hand the MUFU unit to each other explicitly
   float scale_log2;  // scale * log2(e)
@@ -165,7 +167,9 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int qpc = p.q_per_cta;             // query tiles of this CTA: blockIdx.x * qpc + qi
+  const int qt0 = blockIdx.x * qpc, head = blockIdx.y, b = blockIdx.z;
+  const int nq = min(qpc, (p.Sq + 127) / 128 - qt0);
 
   const uint32_t sQ = base;
   const uint32_t sK = base + kStageBytes;
@@ -180,6 +184,8 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
   const uint32_t bar_sfree = bar_sfull + 8;
   const uint32_t bar_pfull = bar_sfree + 8;
   const uint32_t bar_pvdone = bar_pfull + 8;
+  const uint32_t bar_qfree = bar_pvdone + 8;   // Q tile read by its last Q K^T (query-tile loop)
+  const uint32_t bar_ofree = bar_qfree + 8;    // O read by the epilogue of the previous query tile
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bars - base) + 512);
   float* xch = reinterpret_cast<float*>(smem + (bars - base) + 1024);  // [2 parities][2 halves][128 rows]
 
@@ -200,6 +206,8 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
     mbar_init(bar_sfree, 8);
     mbar_init(bar_pfull, 8);
     mbar_init(bar_pvdone, 1);
+    mbar_init(bar_qfree, 1);
+    mbar_init(bar_ofree, 8);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
   // 646 vs 643 TFLOP/s — with two CTAs per SM the SM already has two issuing threads; kept because it shortens the
   // MMA warp's critical path for ND > 1.)
   const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0);
-  auto issue_qk = [&](int t) {
+  auto issue_qk = [&](int t, bool last_of_q) {
     const int s = t % kStages;
     const uint32_t ph = (t / kStages) & 1;
     mbar_wait(bar_kfull + 8 * s, ph);
@@ -235,6 +243,7 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
       }
       umma_commit(bar_kempty + 8 * s);
       umma_commit(bar_sfull);
+      if (last_of_q) umma_commit(bar_qfree);
     }
     __syncwarp();
   };
@@ -242,61 +251,71 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
   if (warp == 0) {
     // converged warp, one ELECTed lane issues (a `lane == 0` branch makes ptxas wrap every uniform-datapath
     // instruction in an ELECT / BRA.U.ANY retry loop)
-    if (elect_one()) {
-      mbar_expect_tx(bar_q, kStageBytes);
-#pragma unroll
-      for (int i = 0; i < ND; ++i) tma_load_4d(sQ + i * kTileBytes, &p.tmQ, bar_q, i * 64, head, qt * 128, b);
-    }
-    __syncwarp();
-    for (int j = 0; j < n; ++j) {
-      const int s = j % kStages;
-      const uint32_t ph = (j / kStages) & 1;
-      mbar_wait(bar_kempty + 8 * s, ph ^ 1u);
+    for (int qi = 0; qi < nq; ++qi) {
+      if (qi > 0) mbar_wait(bar_qfree, (qi - 1) & 1);  // the previous tile's products have read sQ
       if (elect_one()) {
-        mbar_expect_tx(bar_kfull + 8 * s, kStageBytes);
+        mbar_expect_tx(bar_q, kStageBytes);
 #pragma unroll
-        for (int i = 0; i < ND; ++i)
-          tma_load_4d(sK + s * kStageBytes + i * kTileBytes, &p.tmK, bar_kfull + 8 * s, i * 64, head, j * 128, b);
+        for (int i = 0; i < ND; ++i) tma_load_4d(sQ + i * kTileBytes, &p.tmQ, bar_q, i * 64, head, (qt0 + qi) * 128, b);
       }
       __syncwarp();
-      mbar_wait(bar_vempty + 8 * s, ph ^ 1u);
-      if (elect_one()) {
-        mbar_expect_tx(bar_vfull + 8 * s, kStageBytes);
+      for (int j = 0; j < n; ++j) {
+        const int g = qi * n + j;  // tiles of this CTA so far: stages and barrier phases run on
+        const int s = g % kStages;
+        const uint32_t ph = (g / kStages) & 1;
+        mbar_wait(bar_kempty + 8 * s, ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(bar_kfull + 8 * s, kStageBytes);
 #pragma unroll
-        for (int i = 0; i < ND; ++i)
-          tma_load_4d(sV + s * kStageBytes + i * kTileBytes, &p.tmV, bar_vfull + 8 * s, i * 64, head, j * 128, b);
-      }
-      __syncwarp();
-      if (p.split_issue) {
-        if (j == 0) mbar_wait(bar_q, 0);
-        issue_qk(j);
+          for (int i = 0; i < ND; ++i)
+            tma_load_4d(sK + s * kStageBytes + i * kTileBytes, &p.tmK, bar_kfull + 8 * s, i * 64, head, j * 128, b);
+        }
+        __syncwarp();
+        mbar_wait(bar_vempty + 8 * s, ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(bar_vfull + 8 * s, kStageBytes);
+#pragma unroll
+          for (int i = 0; i < ND; ++i)
+            tma_load_4d(sV + s * kStageBytes + i * kTileBytes, &p.tmV, bar_vfull + 8 * s, i * 64, head, j * 128, b);
+        }
+        __syncwarp();
+        if (p.split_issue) {
+          if (j == 0) mbar_wait(bar_q, qi & 1);
+          issue_qk(g, j == n - 1);
+        }
       }
     }
   } else if (warp == 1) {
     const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);  // B (= V) is MN-major
-    mbar_wait(bar_q, 0);
-    if (!p.split_issue) issue_qk(0);
-    for (int j = 0; j < n; ++j) {
-      const int s = j % kStages;
-      const uint32_t ph = (j / kStages) & 1;
-      if (!p.split_issue && j + 1 < n) issue_qk(j + 1);
-      // ---- O += P_j V_j
-      mbar_wait(bar_vfull + 8 * s, ph);
-      mbar_wait(bar_pfull, j & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const int kv_left = p.Skv - j * 128;
-        const int ksteps = kv_left >= 128 ? 8 : (kv_left + 15) >> 4;  // keys beyond Skv contribute nothing
-        for (int k = 0; k < ksteps; ++k) {
+    if (!p.split_issue) {  // single issuing warp (same-box A/B; one query tile per CTA in this mode)
+      mbar_wait(bar_q, 0);
+      issue_qk(0, n == 1);
+    }
+    for (int qi = 0; qi < nq; ++qi) {
+      for (int j = 0; j < n; ++j) {
+        const int g = qi * n + j;
+        const int s = g % kStages;
+        const uint32_t ph = (g / kStages) & 1;
+        if (!p.split_issue && j + 1 < n) issue_qk(j + 1, j + 2 == n);
+        // ---- O += P_j V_j
+        mbar_wait(bar_vfull + 8 * s, ph);
+        mbar_wait(bar_pfull, g & 1);
+        if (j == 0 && qi > 0) mbar_wait(bar_ofree, (qi - 1) & 1);  // the previous tile's O has been read out
+        tc_fence_after();
+        if (elect_one()) {
+          const int kv_left = p.Skv - j * 128;
+          const int ksteps = kv_left >= 128 ? 8 : (kv_left + 15) >> 4;  // keys beyond Skv contribute nothing
+          for (int k = 0; k < ksteps; ++k) {
 #pragma unroll
-          for (int i = 0; i < ND; ++i)
-            umma_ts(tmem_base + kColO + i * 64, tmem_base + kColP + k * 8,
-                    umma_desc_sw128(sV + s * kStageBytes + i * kTileBytes + k * 2048), idesc_pv, (j | k) != 0);
+            for (int i = 0; i < ND; ++i)
+              umma_ts(tmem_base + kColO + i * 64, tmem_base + kColP + k * 8,
+                      umma_desc_sw128(sV + s * kStageBytes + i * kTileBytes + k * 2048), idesc_pv, (j | k) != 0);
+          }
+          umma_commit(bar_vempty + 8 * s);
+          umma_commit(bar_pvdone);
         }
-        umma_commit(bar_vempty + 8 * s);
-        umma_commit(bar_pvdone);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- softmax / correction / store
@@ -309,10 +328,14 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
     const uint32_t tl = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t colS = kColS + half * 64, colP = kColP + half * 32;
     const uint32_t pair_bar = 1 + q;
+    int xc = 0;  // pair exchanges so far (alternating buffers)
+    for (int qi = 0; qi < nq; ++qi) {  // query tiles of this CTA (body not re-indented)
+    const int g0 = qi * n;
     float m_run = -INFINITY;  // running max, already multiplied by scale*log2e
     float l_run = 0.f;        // this warp's share of the row sum
     for (int j = 0; j < n; ++j) {
-      mbar_wait(bar_sfull, j & 1);
+      const int g = g0 + j;   // tiles of this CTA so far: barrier phases run on across query tiles
+      mbar_wait(bar_sfull, g & 1);
       tc_fence_after();
       const int kv_left = p.Skv - j * 128 - half * 64;  // valid keys among this warp's 64 columns (may be <= 0)
       // pass 1: row max over my columns
@@ -342,7 +365,7 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
           }
         }
       }
-      float* xs = xch + ((j & 1) * 2) * 128;
+      float* xs = xch + ((xc++ & 1) * 2) * 128;
       xs[half * 128 + row] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       mx = fmaxf(mx, xs[(half ^ 1) * 128 + row]);
@@ -356,9 +379,9 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
         alpha = fast_exp2(m_run - mx);
         m_run = mx;
       }
-      if (j > 0) {
-        // P_{j-1} has been consumed and O holds the sum over tiles < j
-        mbar_wait(bar_pvdone, (j - 1) & 1);
+      if (g > 0) {
+        // the previous P has been consumed (and, for j > 0, O holds the sum over tiles < j)
+        mbar_wait(bar_pvdone, (g - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {  // identical in both warps of the pair (same rows, same maxima)
           l_run *= alpha;
@@ -428,15 +451,15 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
     // ---- finalize: O / l -> bf16 -> global (only the first d columns of the padded head); each warp of the pair
     // writes its 32 of every 64 O columns
     {
-      float* xs = xch + ((n & 1) * 2) * 128;
+      float* xs = xch + ((xc++ & 1) * 2) * 128;
       xs[half * 128 + row] = l_run;
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       l_run += xs[(half ^ 1) * 128 + row];
     }
-    mbar_wait(bar_pvdone, (n - 1) & 1);
+    mbar_wait(bar_pvdone, (g0 + n - 1) & 1);
     tc_fence_after();
     const float inv = 1.f / l_run;
-    const int srow = qt * 128 + row;
+    const int srow = (qt0 + qi) * 128 + row;
     if (half == 0 && p.lse != nullptr && srow < p.Sq)
       p.lse[(static_cast<size_t>(b) * gridDim.y + head) * p.Sq + srow] = m_run + log2f(l_run);
     __nv_bfloat16* op = p.o + (static_cast<size_t>(b) * p.Sq + srow) * p.ldo + head * p.d;
@@ -462,6 +485,11 @@ __global__ void __launch_bounds__(kAttnThreads, AttnCfg<ND>::kMinBlocks)
         }
       }
     }
+    // O is in registers / on its way out: the next query tile's first P V may overwrite it
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_ofree);
+    }  // query tiles
   }
 
   tc_fence_before();
@@ -942,7 +970,32 @@ extern "C" int sb200_attention(void* handle, void* stream, const void* q, int ld
       }
     }
   }
-  dim3 grid((Sq + 127) / 128, heads, B);
+  // Short key sequences (cross-attention: one key tile): a CTA's fixed cost (launch, TMEM allocation, Q / K / V load
+  // latency, output drain) is several times the work of one 128-query tile, so one CTA walks several consecutive query
+  // tiles of its (batch, head) — the next Q and K / V arrive while the current tile is in the softmax.  The smallest
+  // divisor of the tile count that brings the grid under two CTAs per SM.  Opt-in (SB200_ATTN_QLOOP=1): measured
+  // 31.5 -> 35.3 us (S = 1024, 8 passes), 57.4 -> 68.2 (S = 4096), 43.4 -> 36.6 (d = 40): with single S / P / O
+  // buffers the tiles of one CTA run strictly one after the other (~4.4 us each), and one CTA per SM has nothing to
+  // overlap with, whereas 4.3 waves of independent CTAs, two per SM, hide each other's latencies.
+  const int nq_tiles = (Sq + 127) / 128;
+  p.q_per_cta = 1;
+  {
+    static const bool qloop = [] {
+      const char* e = getenv("SB200_ATTN_QLOOP");
+      return e && e[0] == '1';
+    }();
+    if (qloop && p.split_issue && p.n_kv_tiles == 1 && nq_tiles > 1) {
+      const long long slots = 2LL * ctx->num_sms;
+      int d = nq_tiles;
+      for (int c = 1; c <= nq_tiles; ++c)
+        if (nq_tiles % c == 0 && static_cast<long long>(nq_tiles / c) * heads * B <= slots) {
+          d = c;
+          break;
+        }
+      p.q_per_cta = d;
+    }
+  }
+  dim3 grid((nq_tiles + p.q_per_cta - 1) / p.q_per_cta, heads, B);
   pdl_hint() = static_cast<long long>(grid.x) * grid.y * grid.z <= 4LL * ctx->num_sms;
   if (head_dim <= 64) {
     switch (attn_poly()) {
