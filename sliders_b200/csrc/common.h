@@ -73,14 +73,16 @@ struct Ctx {
 int make_tmap_bf16(Ctx* ctx, CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
 
-// SB200_PDL=0 disables programmatic dependent launch (same-box A/B; default on)
-inline bool pdl_enabled() {
-  static const bool on = [] {
+// SB200_PDL=0 disables programmatic dependent launch, 2 applies it to every launch whatever its size (same-box A/B;
+// default 1: only launches that do not fill the machine, see pdl_hint)
+inline int pdl_mode() {
+  static const int m = [] {
     const char* e = getenv("SB200_PDL");
-    return !(e && e[0] == '0');
+    return e ? atoi(e) : 1;
   }();
-  return on;
+  return m;
 }
+inline bool pdl_enabled() { return pdl_mode() != 0; }
 
 // Per-call hint set by the C-ABI entry points: PDL pays off for small launches (launch latency and prologue are a
 // visible share: +3 % at 2 passes per forward) and costs ~1 % on machine-filling ones (8 passes), so the big shapes
@@ -102,7 +104,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && pdl_hint()) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl_mode() == 2 || (pdl_mode() == 1 && pdl_hint())) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

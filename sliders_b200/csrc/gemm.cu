@@ -974,13 +974,18 @@ static int launch_gemm(Ctx* ctx, cudaStream_t stream, GemmParams& p, int ctas) {
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = csize;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    // programmatic dependent launch like launch_pdl() gives the single-CTA kernel (SB200_PDL_PAIR=0: same-box A/B)
+    static const int pdl_pair = env_int("SB200_PDL_PAIR", 1);
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed =
+        (pdl_pair && (pdl_mode() == 2 || (pdl_mode() == 1 && pdl_hint()))) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
     if (stats)
       SB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<2, true>, p));
     else
