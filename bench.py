@@ -588,6 +588,7 @@ def main():
             eps_cpu = call()
             times.append(time.time() - t1)
         # parity of the kernel path against this very CPU run (same weights, same LoRA, same inputs, same call)
+        net.set_lora_slider(1.0)   # the config-5 sweep above leaves its last slider scale behind
         net.__enter__()
         with torch.no_grad():
             got = train_util.predict_noise_xl(unet, sched, 500, lat1.to(dev), ehs2.to(dev), pooled2.to(dev),
